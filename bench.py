@@ -1,0 +1,324 @@
+"""bench.py — RMCKF 4-feature closed-loop filter-steps/s (BASELINE.json metric) on N B200s.
+
+    python bench.py --gpus 1 --steps 3 --warmup 3                  # this framework
+    python bench.py --impl reference --steps 1 --warmup 0          # reference algorithm on host cores
+    torchrun --nproc-per-node N bench.py --gpus N ...              # one rank per GPU
+
+Workload (BASELINE.json configs[2]): RMCKF (= Method.GMCKF), 4 features (48 states), closed-loop
+kinematic UR10 IBVS, impulsive alpha-stable noise swept over alpha = linspace(1, 2, 12) with
+annealing, T = 300 frames, 100 000 trials per GPU.  One "step" = one pass of the hot path over one
+batch = one kernel launch that runs every trial of the batch through all T frames (+ the
+per-level statistics reduction, + the NCCL all-reduce of those sums when N > 1).  A filter-step
+is one frame of one trial; only frames actually executed are counted.
+
+Prints ONE JSON line (rank 0).  `value` is timed with CUDA events with everything resident on
+the device; `e2e` goes through the host-buffer C-ABI entry point (uvs_closed_loop_host: scratch
+allocation, launch, D2H of the results) per step.
+"""
+import argparse
+import json
+import multiprocessing as mp
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+T_FRAMES = 300
+DT = 0.05
+Q_START = [0.0, 0.0, 1.96349541, 0.0, -1.57079633, 0.0]
+DESIRED_F = [149.0, 145.0, 125.0, 121.0, 101.0, 145.0, 125.0, 169.0]
+SWEEP = [float(v) for v in np.linspace(1.0, 2.0, 12)]
+NOISE_SEED, POSE_SEED = 123456, 12345
+# algorithmic FP64 flops of one RMCKF update with dense X, P, K (m = 8, N = 48)
+M_, N_ = 8, 48
+F_ALG = 4 * N_ ** 2 + 4 * N_ ** 2 * M_ + 4 * N_ * M_ ** 2 + 12 * M_ * N_ + 2 * N_ * M_ + 12 * M_ ** 2 + M_ ** 3 / 3 + 17 * M_
+METRIC = "RMCKF 4-feature closed-loop filter-steps/sec"
+UNIT = "filter-steps/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--mode", default="dense", choices=["dense", "blockdiag"])
+    ap.add_argument("--trials", type=int, default=100_000, help="trials per GPU per step")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-blockdiag-extra", action="store_true")
+    return ap.parse_args()
+
+
+def workload_name(mode, trials):
+    return (f"RMCKF(GMCKF) 4 features / 48 states, closed-loop kinematic UR10 IBVS, alpha-stable noise "
+            f"alpha=linspace(1,2,12) beta=0 gamma=1, annealing, kernel_bw=10, T=300 frames, "
+            f"{trials} trials per GPU per step (BASELINE configs[2]), covariance={mode}")
+
+
+# ------------------------------------------------------------------------- CPU arm (oracle port)
+def _cpu_worker(args):
+    os.environ["OMP_NUM_THREADS"] = os.environ["OPENBLAS_NUM_THREADS"] = os.environ["MKL_NUM_THREADS"] = "1"
+    trial0, n = args
+    from oracle import closed_loop as CL
+    cfg = CL.make_cfg(annealing=True, noise_seed=NOISE_SEED, pose_seed=POSE_SEED)
+    frames = 0
+    t0 = time.perf_counter()
+    for t in range(trial0, trial0 + n):
+        lvl = (t * 12) // 1200 % 12
+        cfg["noise_params"] = dict(alpha=SWEEP[lvl], beta=0.0, gamma=1.0, delta=0.0)
+        frames += CL.run_trial(cfg, t)["frames"]
+    return frames, time.perf_counter() - t0
+
+
+def cpu_sample(trials_per_core, cores=None, trial0=0):
+    """The oracle's as-written NumPy closed loop (experiment.py restated, dense) on all host cores,
+    one single-threaded process per core.  Returns (filter-steps/s aggregate, cores, frames, seconds)."""
+    cores = cores or os.cpu_count() or 1
+    os.environ.setdefault("OMP_NUM_THREADS", "1")
+    os.environ.setdefault("OPENBLAS_NUM_THREADS", "1")
+    ctx = mp.get_context("spawn")
+    jobs = [(trial0 + i * trials_per_core, trials_per_core) for i in range(cores)]
+    t0 = time.perf_counter()
+    with ctx.Pool(cores) as pool:
+        res = pool.map(_cpu_worker, jobs)
+    wall = time.perf_counter() - t0
+    work = max(r[1] for r in res)               # slowest worker = the parallel region without pool start-up
+    frames = sum(r[0] for r in res)
+    return frames / work, cores, frames, wall
+
+
+def run_reference(a):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    tpc = 20
+    for _ in range(a.warmup):
+        cpu_sample(1, cores)
+    vals, ms = [], []
+    for s in range(max(1, a.steps)):
+        v, cores, frames, wall = cpu_sample(tpc, cores, trial0=1000 * s)
+        vals.append(v)
+        ms.append(1e3 * frames / v)
+    value = float(np.mean(vals))
+    sample = f"{cores} processes x {tpc} closed-loop trials x {T_FRAMES} frames per step (as-written NumPy restatement, OMP_NUM_THREADS=1)"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": a.gpus, "steps": max(1, a.steps),
+        "warmup": a.warmup, "ms_per_step": float(np.mean(ms)), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": workload_name("dense (as written)", cores * tpc)},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------- clocks
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.samples, self._stop, self._t = index, [], threading.Event(), None
+
+    def _run(self):
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i",
+                                      str(self.index)], capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.samples.append([c.strip() for c in out.split(",")])
+            except Exception:
+                pass
+            self._stop.wait(0.1)
+
+    def __enter__(self):
+        self._t = threading.Thread(target=self._run, daemon=True)
+        self._t.start()
+        return self
+
+    def __exit__(self, *exc):
+        self._stop.set()
+        self._t.join(timeout=6)
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        sm = [float(s[0]) for s in self.samples if s[0].replace(".", "").isdigit()]
+        mx = [float(s[1]) for s in self.samples if s[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(s[3 + i].lower().startswith("active") for s in self.samples)]
+        pw = [float(s[2]) for s in self.samples if s[2].replace(".", "").isdigit()]
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(pw) if pw else None, "samples": len(self.samples), "reasons": reasons}
+
+
+# ------------------------------------------------------------------------- GPU arm
+def run_ours(a):
+    import torch
+    import torch.distributed as dist
+    import uvs_b200 as uvs
+    L, E = uvs._lib, uvs.engine
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    B = a.trials
+    trial0 = rank * B                      # contiguous trial shard per rank; Philox keyed by global trial id
+    n_levels = len(SWEEP)
+    epoch = (world * B + n_levels - 1) // n_levels
+
+    def make_cfg(mode):
+        p = E.filter_params(L.METHOD_GMCKF, 4, mode=L.MODE_DENSE if mode == "dense" else L.MODE_BLOCKDIAG,
+                            kernel_bw=10.0, annealing=True)
+        return E.closed_loop_cfg(p, E.noise_params(L.NOISE_ALPHA_STABLE, seed=NOISE_SEED, alpha=1.5, beta=0.0,
+                                                   gamma=1.0, delta=0.0),
+                                 T=T_FRAMES, dt=DT, ibvs_gain=0.2, q_start=Q_START, desired_f=DESIRED_F,
+                                 pose_seed=POSE_SEED, sweep=SWEEP, sweep_epoch=epoch, sweep_param=2)
+
+    flush = torch.empty(256 * 1024 * 1024 // 8, dtype=torch.float64, device="cuda")   # > 126 MB L2
+
+    def step(cfg, out):
+        E.closed_loop(cfg, trial0, B, out=out)
+        sums, n_fail = E.reduce_stats(out["stats"], out["status"], trial0, epoch, n_levels)
+        if world > 1:
+            dist.all_reduce(sums)
+            dist.all_reduce(n_fail)
+        return sums, n_fail
+
+    def timed(mode, steps, warmup):
+        cfg = make_cfg(mode)
+        out = E.closed_loop(cfg, trial0, B)             # allocates the result buffers once
+        for _ in range(max(0, warmup - 1)):
+            step(cfg, out)
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ks, ke = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        kernel_ms = []
+        e0.record()
+        for _ in range(steps):
+            flush.fill_(0.0)                              # L2 flush between timed iterations
+            ks.record()
+            E.closed_loop(cfg, trial0, B, out=out)
+            ke.record()
+            sums, n_fail = E.reduce_stats(out["stats"], out["status"], trial0, epoch, n_levels)
+            if world > 1:
+                dist.all_reduce(sums)
+                dist.all_reduce(n_fail)
+            ke.synchronize()
+            kernel_ms.append(ks.elapsed_time(ke))
+        e1.record()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        frames = out["frames"].sum(dtype=torch.int64)
+        t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dist.all_reduce(frames)
+        return dict(ms_total=float(t.item()), frames=int(frames.item()), kernel_ms=float(np.mean(kernel_ms)),
+                    sums=sums.cpu().numpy(), n_fail=n_fail.cpu().numpy(), local_frames=int(out["frames"].sum().item()))
+
+    with ClockSampler(local) as clocks:
+        main = timed(a.mode, a.steps, a.warmup)
+    value = main["frames"] * a.steps / (main["ms_total"] * 1e-3)
+
+    # end-to-end through the host-buffer C-ABI entry point (per step: scratch alloc, launch, D2H, sync)
+    cfg = make_cfg(a.mode)
+    E.closed_loop_host(cfg, trial0, min(B, 4096))
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    e2e_frames = 0
+    for _ in range(a.steps):
+        st, status, frames = E.closed_loop_host(cfg, trial0, B)
+        e2e_frames += int(frames.sum())
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    tt = torch.tensor([e2e_s, float(e2e_frames)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        tmax = tt.clone()
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        dist.all_reduce(tt)
+        e2e_value = float(tt[1].item() / tmax[0].item())
+    else:
+        e2e_value = e2e_frames / e2e_s
+    h2d = int(__import__("ctypes").sizeof(L.ClosedLoopCfg))
+    d2h = B * (3 * 8 + 4 + 4)
+
+    extra = None
+    if not a.no_blockdiag_extra and a.mode == "dense":
+        bd = timed("blockdiag", max(1, a.steps), 2)
+        extra = {"value": bd["frames"] * max(1, a.steps) / (bd["ms_total"] * 1e-3), "unit": UNIT,
+                 "note": "block-diagonal family (exact for the reference's P0=Q=I, R=I); its own executed flops "
+                         "are ~5e3 per step, never multiplied by F_alg"}
+
+    peak_tf, _ = E.fp64_peak(4096)
+    peak_tf = max(peak_tf, E.fp64_peak(4096)[0])
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    steps_per_launch = main["local_frames"]
+    achieved = steps_per_launch * F_ALG / (main["kernel_ms"] * 1e-3) / 1e12
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
+        "ms_per_step": main["ms_total"] / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {"workload": workload_name(a.mode, B), "trials_per_gpu": B, "frames": T_FRAMES,
+                   "l2": "256 MB buffer written between timed iterations; filter state is shared-memory resident, "
+                         "the only HBM traffic is 32 B of results per trial",
+                   "noise_seed": NOISE_SEED, "pose_seed": POSE_SEED},
+        "clocks": clocks.summary(),
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "api": "uvs_closed_loop_host (C ABI, host result buffers)"},
+        "gpu_launches": 2 * a.steps,
+        "roofline": {"bound": "fp64", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s",
+                     "frac": achieved / peak_tf, "traffic": None,
+                     "kernel": f"{a.mode}_closed_loop_kernel<8, GMCKF>", "kernel_ms": main["kernel_ms"],
+                     "flops_per_filter_step_algorithmic": F_ALG,
+                     "peak_source": "measured in this run: uvs_fp64_peak (register-resident DFMA chains on every SM); "
+                                    "MEASURED_PEAKS.json has no FP64 entry; datasheet 148 SM x 64 lanes x 2 x 1.965 GHz = 37.2"},
+        "failed_trials": float(main["n_fail"].sum()),
+        "itae_mean_per_level": [float(s[2, 1] / max(s[2, 0], 1.0)) for s in main["sums"]],
+    }
+    if extra:
+        line["blockdiag"] = extra
+    if not a.no_cpu_baseline and world == 1:
+        v, cores, frames, wall = cpu_sample(20)
+        line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
+                                "sample": f"{cores} processes x 20 closed-loop trials x {T_FRAMES} frames "
+                                          f"(oracle as-written NumPy restatement of experiment.py, 1 BLAS thread each; {wall:.1f} s wall)"}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    a = parse()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_ours(a)
+
+
+if __name__ == "__main__":
+    main()

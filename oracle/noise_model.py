@@ -13,8 +13,8 @@ Counter layout (shared with csrc/philox.cuh):
     key = (seed & 0xffffffff, seed >> 32)
     ctr = (trial & 0xffffffff, trial >> 32, frame, (purpose << 16) | (draw << 8) | coord)
     purpose: 0 = feature noise, 1 = start-pose perturbation, 2 = random X0
-One call yields r0..r3; ua = open53(r0 | r1 << 32), ub = open53(r2 | r3 << 32),
-open53(x) = ((x >> 11) + 0.5) * 2**-53  in (0, 1).
+One call yields r0..r3; ua = open52(r0 | r1 << 32), ub = open52(r2 | r3 << 32),
+open52(x) = ((x >> 12) + 0.5) * 2**-52  in (0, 1)  (exact in FP64, never 0 or 1).
 """
 import numpy as np
 
@@ -54,9 +54,9 @@ def philox4x32_10(c0, c1, c2, c3, k0, k1):
     return tuple(a.astype(np.uint32) for a in (c0, c1, c2, c3))
 
 
-def _open53(lo, hi):
+def _open52(lo, hi):
     x = lo.astype(np.uint64) | (hi.astype(np.uint64) << np.uint64(32))
-    return ((x >> np.uint64(11)).astype(np.float64) + 0.5) * (2.0 ** -53)
+    return ((x >> np.uint64(12)).astype(np.float64) + 0.5) * (2.0 ** -52)
 
 
 def uniforms(seed, trial, frame, coord, draw=0, purpose=PURPOSE_NOISE):
@@ -69,7 +69,7 @@ def uniforms(seed, trial, frame, coord, draw=0, purpose=PURPOSE_NOISE):
     c3 = (np.uint32(purpose << 16) | np.uint32(draw << 8)) | np.asarray(coord, dtype=np.uint32)
     r0, r1, r2, r3 = philox4x32_10(c0, c1, c2, c3,
                                    np.uint32(seed & 0xFFFFFFFF), np.uint32((seed >> 32) & 0xFFFFFFFF))
-    return _open53(r0, r1), _open53(r2, r3)
+    return _open52(r0, r1), _open52(r2, r3)
 
 
 def _box_muller(ua, ub):

@@ -1,0 +1,74 @@
+"""CPU: the C-ABI library loads, exports every symbol include/uvs_b200.h declares, and the ctypes
+mirror of its structs has the C layout.  No compute calls (no GPU here)."""
+import ctypes as C
+import os
+import re
+import subprocess
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = os.path.join(ROOT, "include", "uvs_b200.h")
+
+
+@pytest.fixture(scope="module")
+def lib():
+    import __graft_entry__ as ge
+    ge.build()
+    import uvs_b200
+    return uvs_b200._lib
+
+
+def test_every_declared_symbol_is_exported(lib):
+    text = open(HEADER).read()
+    declared = set(re.findall(r"^int\s+(uvs_\w+)\s*\(", text, flags=re.M))
+    assert len(declared) >= 15
+    handle = lib.load()
+    for name in declared:
+        assert hasattr(handle, name), name
+    assert declared == set(lib.EXPORTED)
+    assert handle.uvs_version() == 1
+
+
+def test_struct_layout_matches_c(lib, tmp_path):
+    src = tmp_path / "sz.c"
+    src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "uvs_b200.h"\n'
+                   'int main(){printf("%zu %zu %zu %zu %zu %zu %zu\\n", sizeof(uvs_filter_params), sizeof(uvs_noise_params),'
+                   'sizeof(uvs_closed_loop_cfg), sizeof(uvs_closed_loop_io), offsetof(uvs_closed_loop_cfg, sweep),'
+                   'offsetof(uvs_closed_loop_cfg, P0), offsetof(uvs_closed_loop_io, p_layout));return 0;}\n')
+    exe = tmp_path / "sz"
+    subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)])
+    got = [int(v) for v in subprocess.check_output([str(exe)]).split()]
+    want = [C.sizeof(lib.FilterParams), C.sizeof(lib.NoiseParams), C.sizeof(lib.ClosedLoopCfg),
+            C.sizeof(lib.ClosedLoopIO), lib.ClosedLoopCfg.sweep.offset, lib.ClosedLoopCfg.P0.offset,
+            lib.ClosedLoopIO.p_layout.offset]
+    assert got == want
+
+
+def test_errors_are_reported_not_raised_across_the_boundary(lib):
+    handle = lib.load()
+    rc = handle.uvs_ibvs(2, 1, None, None, None, 0.2, None, None, None)      # nf = 2 is not a scene
+    assert rc == -1
+    assert "nf" in lib.last_error()
+    p = lib.FilterParams()
+    p.method, p.nf = 1, 4                                                    # ANALYTICAL is not a filter
+    rc = handle.uvs_filter_step(C.byref(p), 1, 8, 8, 0, 8, 8, 1.0, None, None, None, None)
+    assert rc == -1 and "method" in lib.last_error()
+
+
+def test_product_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "uncalibrated-visual-servoing_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for fn in files:
+            if fn.endswith((".py", ".cu", ".cuh", ".h")):
+                text = open(os.path.join(dirpath, fn)).read()
+                assert "oracle" not in text.replace("oracle/noise_model.py", ""), fn
+
+
+def test_host_layer_fails_loudly_without_gpu(lib):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    import uvs_b200
+    with pytest.raises(lib.UvsError):
+        uvs_b200.engine.fp64_peak()

@@ -1,0 +1,60 @@
+"""Builds libuvs_b200.so (the C-ABI CUDA library) in-tree with nvcc for sm_100a.
+
+    python uncalibrated-visual-servoing_b200/build.py [--force] [--verbose]
+
+One object per .cu (compiled in parallel), linked with the static CUDA runtime so the
+library has no dependency on torch or on a system libcudart.  -lineinfo keeps ncu's
+source page usable.
+"""
+import concurrent.futures as cf
+import os
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+OBJ = os.path.join(HERE, "build")
+LIB = os.path.join(HERE, "libuvs_b200.so")
+SOURCES = ["api.cu", "aux_kernels.cu", "blockdiag_kernels.cu", "dense_m2.cu", "dense_m6.cu", "dense_m8.cu"]
+NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
+         "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", "--expt-relaxed-constexpr",
+         "-Xptxas", "-v"]
+
+
+def _deps():
+    return [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + \
+           [os.path.join(os.path.dirname(HERE), "include", "uvs_b200.h"), os.path.abspath(__file__)]
+
+
+def _compile(src, verbose):
+    obj = os.path.join(OBJ, src.replace(".cu", ".o"))
+    cmd = [NVCC] + FLAGS + ["-c", os.path.join(CSRC, src), "-o", obj]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    log = os.path.join(OBJ, src.replace(".cu", ".ptxas.log"))
+    with open(log, "w") as fh:
+        fh.write(r.stderr)
+    if r.returncode != 0:
+        raise RuntimeError(f"nvcc failed on {src}:\n{r.stdout}\n{r.stderr}")
+    if verbose:
+        print(r.stderr)
+    return obj
+
+
+def build(force=False, verbose=False):
+    os.makedirs(OBJ, exist_ok=True)
+    if not force and os.path.exists(LIB):
+        newest = max(os.path.getmtime(p) for p in _deps())
+        if os.path.getmtime(LIB) >= newest:
+            return LIB
+    with cf.ThreadPoolExecutor(max_workers=min(8, len(SOURCES))) as ex:
+        objs = list(ex.map(lambda s: _compile(s, verbose), SOURCES))
+    cmd = [NVCC, "-shared", "-o", LIB] + objs + ["-gencode", "arch=compute_100a,code=sm_100a", "-cudart", "static"]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
+    return LIB
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv))

@@ -1,0 +1,295 @@
+// api.cu — the extern "C" boundary of libuvs_b200.so (declared in include/uvs_b200.h).
+// Argument validation, kernel-family selection, launch geometry, error plumbing.
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+
+#include "aux_kernels.h"
+#include "blockdiag_kernels.h"
+#include "dense_kernels.cuh"
+
+namespace uvs {
+
+static thread_local char g_err[512] = "";
+
+int set_error(int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+int check_cuda(cudaError_t e, const char* what) {
+    if (e == cudaSuccess) return 0;
+    return set_error(UVS_ERR_CUDA, "%s: %s", what, cudaGetErrorString(e));
+}
+
+struct DeviceInfo {
+    int device = -1, sms = 0, major = 0, minor = 0, clock_khz = 0;
+    size_t smem_optin = 0;
+};
+
+static int device_info(DeviceInfo& d) {
+    static thread_local DeviceInfo cache;
+    int dev = 0;
+    if (int rc = check_cuda(cudaGetDevice(&dev), "cudaGetDevice")) return rc;
+    if (cache.device != dev) {
+        cudaDeviceProp p;
+        if (int rc = check_cuda(cudaGetDeviceProperties(&p, dev), "cudaGetDeviceProperties")) return rc;
+        cache.device = dev;
+        cache.sms = p.multiProcessorCount;
+        cache.major = p.major;
+        cache.minor = p.minor;
+        cache.smem_optin = p.sharedMemPerBlockOptin;
+        int khz = 0;
+        cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, dev);
+        cache.clock_khz = khz;
+    }
+    d = cache;
+    return 0;
+}
+
+static bool valid_nf(int nf) { return nf == 1 || nf == 3 || nf == 4; }
+static bool valid_method(int m) { return m >= UVS_METHOD_KF && m <= UVS_METHOD_GMCKF; }
+
+// kernel family for a request: blockdiag needs identity/NULL Q and R and block P
+static int resolve_mode(const uvs_filter_params& fp, bool p_is_blocks_or_identity) {
+    if (fp.mode == UVS_MODE_DENSE) return UVS_MODE_DENSE;
+    const bool can = (fp.Q == nullptr) && (fp.R == nullptr) && p_is_blocks_or_identity;
+    if (fp.mode == UVS_MODE_BLOCKDIAG) return can ? UVS_MODE_BLOCKDIAG : -1;
+    return can ? UVS_MODE_BLOCKDIAG : UVS_MODE_DENSE;
+}
+
+// launch geometry of the dense family: as many warps per CTA as shared memory allows (<= 10)
+static int dense_geometry(int m, int method, long long B, const DeviceInfo& d, int& grid, int& block) {
+    size_t per0, per1;
+    switch (m) {
+    case 2: per0 = dense_ws_bytes<2>(method, 0); per1 = dense_ws_bytes<2>(method, 1); break;
+    case 6: per0 = dense_ws_bytes<6>(method, 0); per1 = dense_ws_bytes<6>(method, 1); break;
+    case 8: per0 = dense_ws_bytes<8>(method, 0); per1 = dense_ws_bytes<8>(method, 1); break;
+    default: return set_error(UVS_ERR_INVALID, "m=%d", m);
+    }
+    const size_t per_warp = per1 - per0;
+    int warps = (int)((d.smem_optin - per0) / per_warp);
+    if (warps > 10) warps = 10;
+    if (warps < 1) return set_error(UVS_ERR_UNSUPPORTED, "workspace does not fit shared memory");
+    // two CTAs per SM when both fit (smaller m): halves the tail
+    int ctas_per_sm = 1;
+    if (2 * (per0 + warps * per_warp + 1024) <= 228 * 1024 && warps * 2 * 32 <= 2048) ctas_per_sm = 2;
+    long long need = (B + warps - 1) / warps;
+    long long g = (long long)d.sms * ctas_per_sm;
+    if (need < g) g = need;
+    if (g < 1) g = 1;
+    if (B < warps) warps = (int)B;
+    grid = (int)g;
+    block = warps * 32;
+    return 0;
+}
+
+}  // namespace uvs
+
+using namespace uvs;
+
+#pragma GCC visibility push(default)
+extern "C" {
+
+int uvs_version(void) { return UVS_ABI_VERSION; }
+
+int uvs_last_error(char* buf, size_t n) {
+    if (!buf || n == 0) return UVS_ERR_INVALID;
+    strncpy(buf, g_err, n - 1);
+    buf[n - 1] = 0;
+    return 0;
+}
+
+int uvs_device_info(int* sm_count, int* cc_major, int* cc_minor, int* sm_clock_khz) {
+    DeviceInfo d;
+    if (int rc = device_info(d)) return rc;
+    if (sm_count) *sm_count = d.sms;
+    if (cc_major) *cc_major = d.major;
+    if (cc_minor) *cc_minor = d.minor;
+    if (sm_clock_khz) *sm_clock_khz = d.clock_khz;
+    return 0;
+}
+
+static int run_replay(ReplayArgs& a, void* stream) {
+    const uvs_filter_params& fp = a.fp;
+    if (!valid_nf(fp.nf)) return set_error(UVS_ERR_INVALID, "nf must be 1, 3 or 4 (got %d)", fp.nf);
+    if (!valid_method(fp.method)) return set_error(UVS_ERR_INVALID, "method %d is not a filter method", fp.method);
+    if (a.B < 0 || a.T < 1) return set_error(UVS_ERR_INVALID, "B=%lld T=%d", a.B, a.T);
+    if (a.p_layout != UVS_P_DENSE && a.p_layout != UVS_P_BLOCKS) return set_error(UVS_ERR_INVALID, "p_layout");
+    if (!fp.joseph && fp.method == UVS_METHOD_MCKF)
+        return set_error(UVS_ERR_UNSUPPORTED, "MCKF requires the Joseph update (tests/mckf_*.py use it too)");
+    if (a.B == 0) return 0;
+    DeviceInfo d;
+    if (int rc = device_info(d)) return rc;
+    const int m = 2 * fp.nf;
+    // the block family needs P given as blocks (or identity) and does not expose K
+    const int mode = resolve_mode(fp, (a.p_layout == UVS_P_BLOCKS || a.P == nullptr) && a.K_out == nullptr);
+    if (mode < 0) return set_error(UVS_ERR_INVALID, "UVS_MODE_BLOCKDIAG needs Q = R = NULL, a block P and no K_out");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (mode == UVS_MODE_BLOCKDIAG) return check_cuda(launch_blockdiag_replay(m, a, d.sms, st), "blockdiag replay");
+    int grid, block;
+    if (int rc = dense_geometry(m, fp.method, a.B, d, grid, block)) return rc;
+    cudaError_t e;
+    switch (m) {
+    case 2: e = launch_dense_replay<2>(a, grid, block, st); break;
+    case 6: e = launch_dense_replay<6>(a, grid, block, st); break;
+    default: e = launch_dense_replay<8>(a, grid, block, st); break;
+    }
+    return check_cuda(e, "dense replay launch");
+}
+
+int uvs_filter_step(const uvs_filter_params* p, int64_t B, double* X, double* P, int p_layout,
+                    const double* h, const double* Z, double sigma,
+                    double* K_out, double* kappa_out, int32_t* flags_out, void* stream) {
+    if (!p || !X || !P || !h || !Z) return set_error(UVS_ERR_INVALID, "uvs_filter_step: NULL argument");
+    ReplayArgs a{};
+    a.fp = *p; a.B = B; a.T = 1; a.k_max = 1; a.direct = 1; a.p_layout = p_layout; a.sigma = sigma;
+    a.h = h; a.Z = Z; a.X = X; a.P = P; a.K_out = K_out; a.kappa_out = kappa_out; a.flags_out = flags_out;
+    return run_replay(a, stream);
+}
+
+int uvs_replay(const uvs_filter_params* p, int64_t B, int32_t T, int32_t k_max,
+               const double* f, const double* dq, const double* f_init,
+               double* X, double* P, int p_layout,
+               double* X_out, double* P_out, double* kappa_out, int32_t* flags_out, void* stream) {
+    if (!p || !f || !dq || !f_init || !X) return set_error(UVS_ERR_INVALID, "uvs_replay: NULL argument");
+    ReplayArgs a{};
+    a.fp = *p; a.B = B; a.T = T; a.k_max = k_max > 0 ? k_max : T; a.direct = 0; a.p_layout = p_layout;
+    a.f = f; a.dq = dq; a.f_init = f_init; a.X = X; a.P = P;
+    a.X_out = X_out; a.P_out = P_out; a.kappa_out = kappa_out; a.flags_out = flags_out;
+    return run_replay(a, stream);
+}
+
+int uvs_ibvs(int32_t nf, int64_t B, const double* J, const double* e, const double* kappa, double gain,
+             double* dq_out, int32_t* flags_out, void* stream) {
+    if (!valid_nf(nf)) return set_error(UVS_ERR_INVALID, "nf must be 1, 3 or 4 (got %d)", nf);
+    if (!J || !e || !dq_out || B < 0) return set_error(UVS_ERR_INVALID, "uvs_ibvs: bad argument");
+    if (B == 0) return 0;
+    return check_cuda(launch_ibvs(2 * nf, B, J, e, kappa, gain, dq_out, flags_out, (cudaStream_t)stream), "ibvs");
+}
+
+int uvs_ur10_fk(int64_t B, const double* q, double* T06_out, double* Jgeom_out, void* stream) {
+    if (!q || B < 0) return set_error(UVS_ERR_INVALID, "uvs_ur10_fk: bad argument");
+    if (B == 0) return 0;
+    return check_cuda(launch_fk(B, q, T06_out, Jgeom_out, (cudaStream_t)stream), "ur10_fk");
+}
+
+int uvs_project(int32_t nf, int64_t B, const double* q, const double* targets_host,
+                double* f_out, double* depth_out, void* stream) {
+    if (!valid_nf(nf) || !q || !targets_host || B < 0) return set_error(UVS_ERR_INVALID, "uvs_project: bad argument");
+    if (B == 0) return 0;
+    return check_cuda(launch_project(nf, B, q, targets_host, f_out, depth_out, nullptr, (cudaStream_t)stream),
+                      "project");
+}
+
+int uvs_initial_guess(int32_t nf, int64_t B, const double* q, const double* targets_host,
+                      double* X0_out, double* f_out, void* stream) {
+    if (!valid_nf(nf) || !q || !targets_host || !X0_out || B < 0)
+        return set_error(UVS_ERR_INVALID, "uvs_initial_guess: bad argument");
+    if (B == 0) return 0;
+    return check_cuda(launch_project(nf, B, q, targets_host, f_out, nullptr, X0_out, (cudaStream_t)stream),
+                      "initial_guess");
+}
+
+static int check_noise(const uvs_noise_params& np) {
+    if (np.type < UVS_NOISE_NONE || np.type > UVS_NOISE_UNIFORM) return set_error(UVS_ERR_INVALID, "noise type %d", np.type);
+    if (np.type == UVS_NOISE_ALPHA_STABLE && !(np.alpha > 0.0 && np.alpha <= 2.0))
+        return set_error(UVS_ERR_INVALID, "alpha-stable needs 0 < alpha <= 2 (got %g)", np.alpha);
+    if (np.hold_cnt < 0) return set_error(UVS_ERR_INVALID, "hold_cnt < 0");
+    return 0;
+}
+
+int uvs_noise_fill(const uvs_noise_params* np, uint64_t trial0, int64_t B, int32_t T, int32_t m,
+                   double* out, void* stream) {
+    if (!np || !out || B < 0 || T < 0 || m < 2 || (m & 1)) return set_error(UVS_ERR_INVALID, "uvs_noise_fill: bad argument");
+    if (int rc = check_noise(*np)) return rc;
+    if (B == 0 || T == 0) return 0;
+    return check_cuda(launch_noise_fill(*np, trial0, B, T, m, out, (cudaStream_t)stream), "noise_fill");
+}
+
+int uvs_start_poses(const double* q_start_host, uint64_t pose_seed, int32_t change_q_start,
+                    uint64_t trial0, int64_t B, double* q_out, void* stream) {
+    if (!q_start_host || !q_out || B < 0) return set_error(UVS_ERR_INVALID, "uvs_start_poses: bad argument");
+    if (B == 0) return 0;
+    return check_cuda(launch_start_poses(q_start_host, pose_seed, change_q_start, trial0, B, q_out,
+                                         (cudaStream_t)stream), "start_poses");
+}
+
+int uvs_closed_loop(const uvs_closed_loop_cfg* cfg, uint64_t trial0, int64_t B,
+                    const uvs_closed_loop_io* io, void* stream) {
+    if (!cfg || !io || !io->stats || !io->status) return set_error(UVS_ERR_INVALID, "uvs_closed_loop: NULL argument");
+    const uvs_filter_params& fp = cfg->filt;
+    if (!valid_nf(fp.nf)) return set_error(UVS_ERR_INVALID, "nf must be 1, 3 or 4 (got %d)", fp.nf);
+    if (!valid_method(fp.method)) return set_error(UVS_ERR_INVALID, "method %d is not a filter method", fp.method);
+    if (cfg->T < 1 || B < 0) return set_error(UVS_ERR_INVALID, "T=%d B=%lld", cfg->T, (long long)B);
+    if (cfg->sweep_len < 0 || cfg->sweep_len > UVS_MAX_SWEEP) return set_error(UVS_ERR_INVALID, "sweep_len");
+    if (!fp.joseph && fp.method == UVS_METHOD_MCKF)
+        return set_error(UVS_ERR_UNSUPPORTED, "MCKF requires the Joseph update");
+    if (int rc = check_noise(cfg->noise)) return rc;
+    if (B == 0) return 0;
+    DeviceInfo d;
+    if (int rc = device_info(d)) return rc;
+    const int m = 2 * fp.nf;
+    const int mode = resolve_mode(fp, cfg->P0 == nullptr);
+    if (mode < 0) return set_error(UVS_ERR_INVALID, "UVS_MODE_BLOCKDIAG needs Q = R = P0 = NULL");
+    ClosedLoopArgs a{};
+    a.cfg = *cfg; a.io = *io; a.trial0 = trial0; a.B = B;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (mode == UVS_MODE_BLOCKDIAG) return check_cuda(launch_blockdiag_closed_loop(m, a, d.sms, st), "blockdiag closed loop");
+    int grid, block;
+    if (int rc = dense_geometry(m, fp.method, B, d, grid, block)) return rc;
+    cudaError_t e;
+    switch (m) {
+    case 2: e = launch_dense_closed_loop<2>(a, grid, block, st); break;
+    case 6: e = launch_dense_closed_loop<6>(a, grid, block, st); break;
+    default: e = launch_dense_closed_loop<8>(a, grid, block, st); break;
+    }
+    return check_cuda(e, "dense closed-loop launch");
+}
+
+int uvs_closed_loop_host(const uvs_closed_loop_cfg* cfg, uint64_t trial0, int64_t B,
+                         double* stats_host, int32_t* status_host, int32_t* frames_host) {
+    if (!cfg || !stats_host || !status_host || B < 0) return set_error(UVS_ERR_INVALID, "uvs_closed_loop_host: bad argument");
+    if (B == 0) return 0;
+    double* d_stats = nullptr;
+    int32_t *d_status = nullptr, *d_frames = nullptr;
+    int rc = check_cuda(cudaMalloc(&d_stats, sizeof(double) * 3 * B), "cudaMalloc stats");
+    if (!rc) rc = check_cuda(cudaMalloc(&d_status, sizeof(int32_t) * B), "cudaMalloc status");
+    if (!rc) rc = check_cuda(cudaMalloc(&d_frames, sizeof(int32_t) * B), "cudaMalloc frames");
+    if (!rc) {
+        uvs_closed_loop_io io{};
+        io.stats = d_stats; io.status = d_status; io.frames = d_frames;
+        rc = uvs_closed_loop(cfg, trial0, B, &io, nullptr);
+    }
+    if (!rc) rc = check_cuda(cudaMemcpy(stats_host, d_stats, sizeof(double) * 3 * B, cudaMemcpyDeviceToHost), "D2H stats");
+    if (!rc) rc = check_cuda(cudaMemcpy(status_host, d_status, sizeof(int32_t) * B, cudaMemcpyDeviceToHost), "D2H status");
+    if (!rc && frames_host)
+        rc = check_cuda(cudaMemcpy(frames_host, d_frames, sizeof(int32_t) * B, cudaMemcpyDeviceToHost), "D2H frames");
+    cudaFree(d_stats); cudaFree(d_status); cudaFree(d_frames);
+    return rc;
+}
+
+int uvs_reduce_stats(int64_t B, uint64_t trial0, int32_t sweep_epoch, int32_t n_levels,
+                     const double* stats, const int32_t* status, double* sums, double* n_fail, void* stream) {
+    if (!stats || !status || !sums || !n_fail || B < 0 || n_levels < 1 || n_levels > 4096)
+        return set_error(UVS_ERR_INVALID, "uvs_reduce_stats: bad argument");
+    if (B == 0) return 0;
+    return check_cuda(launch_reduce_stats(B, trial0, sweep_epoch, n_levels, stats, status, sums, n_fail,
+                                          (cudaStream_t)stream), "reduce_stats");
+}
+
+int uvs_fp64_peak(int32_t iters, double* tflops_host, double* ms_host) {
+    if (!tflops_host || iters < 1) return set_error(UVS_ERR_INVALID, "uvs_fp64_peak: bad argument");
+    DeviceInfo d;
+    if (int rc = device_info(d)) return rc;
+    double ms = 0.0;
+    int rc = check_cuda(run_fp64_peak(iters, d.sms, tflops_host, &ms), "fp64 peak probe");
+    if (ms_host) *ms_host = ms;
+    return rc;
+}
+
+}  // extern "C"
+#pragma GCC visibility pop

@@ -1,0 +1,660 @@
+// dense.cuh — one filter per warp, general SPD covariance.
+//
+// Replaces /root/reference/experiment.py:166-297 (predict, KF / MCKF / IMCC-KF / GMCKF=RMCKF
+// update, Joseph covariance update) for B independent filters.
+//
+// Data layout (per warp, in shared memory — the filter never touches HBM between frames):
+//   P    symmetric N x N stored as its M(M+1)/2 lower 6x6 blocks, each block row-major and padded
+//        to 38 doubles so that 32 lanes reading 32 different blocks with 128-bit loads hit 32
+//        different bank groups.  Diagonal blocks are kept full (both triangles identical).
+//   At   (P H^T)^T, Kt = K^T, Ut = U^T : M x N, "k-major", so a lane's 6 consecutive rows of one
+//        column are one 48-byte run (three LDS.128, broadcast across lanes sharing a block row).
+//   X    N state;  S, D  M x M.
+//
+// Algebra (H = I_M (x) h^T, A = P^- H^T, S0 = H A):
+//   KF      S = S0 + R          K = A S^-1            U = A
+//   GMCKF   S = S0 + Rh         K = A S^-1            U = A + K (Rh - R)     Rh = Br (C + 1e-6 I)^-1 Br^T
+//   IMCCKF  S = c S0 + R        K = c A S^-1          U = A + (1 - c) (A S^-1) R
+//   then    P = P^- - K U^T   (== Joseph form (I-KH)P(I-KH)^T + K R K^T exactly, because A = K S
+//           up to the factor c; rank-M update on the lower blocks only)
+//   MCKF    fixed point on (Cx, Cy); the last gain K is not of the form A S^-1, so the Joseph form
+//           is evaluated as the symmetric rank-2M update  P = P^- - K V^T - V K^T,  V = A - K (S0+R)/2.
+//   joseph = 0 (tests/kalman_*): P = (I - K H) P^- = P^- - K A^T.
+#pragma once
+#include "common.cuh"
+#include "smallmat.cuh"
+
+namespace uvs {
+
+constexpr int kBlkStride = 38;
+
+template <int M>
+struct DenseConsts {          // per CTA
+    double R[M * M];
+    double Br[M * M];         // chol(R) lower, full storage
+    double Brinv[M * M];      // inverse of Br (lower)
+    int r_identity;
+    int q_identity;
+};
+
+template <int M, bool MCKF>
+struct DenseWS {
+    static constexpr int N = 6 * M;
+    static constexpr int NB = M * (M + 1) / 2;
+    double P[NB * kBlkStride];
+    double At[M * N];
+    double Kt[M * N];
+    double Ut[M * N];
+    double X[N];
+    double S[M * M];
+    double D[M * M];
+    double ib[56];                              // weights / IBVS scratch (G 21, g 6, b 8, res 8, x 6)
+    double Lp[MCKF ? NB * kBlkStride : 2];      // chol(P) in the same block layout
+    double Xc[MCKF ? N : 2];
+    double dx[MCKF ? N : 2];                    // X - Xc, then ex, then 1/cx
+};
+
+UVS_DEV int blk_index(int bi, int bj) { return bi * (bi + 1) / 2 + bj; }
+
+// lane -> off-diagonal block (bi > bj)
+UVS_DEV void offdiag_of_lane(int lane, int& bi, int& bj) {
+    int i = 1;
+    while ((i + 1) * i / 2 <= lane) ++i;        // smallest i with i(i+1)/2 > lane
+    bi = i;
+    bj = lane - i * (i - 1) / 2;
+}
+
+UVS_DEV void load_block(const double* p, double (&B)[6][6]) {
+    const double2* p2 = reinterpret_cast<const double2*>(p);
+#pragma unroll
+    for (int i = 0; i < 18; ++i) {
+        const double2 v = p2[i];
+        B[(2 * i) / 6][(2 * i) % 6] = v.x;
+        B[(2 * i + 1) / 6][(2 * i + 1) % 6] = v.y;
+    }
+}
+
+UVS_DEV void store_block(double* p, const double (&B)[6][6]) {
+    double2* p2 = reinterpret_cast<double2*>(p);
+#pragma unroll
+    for (int i = 0; i < 18; ++i)
+        p2[i] = make_double2(B[(2 * i) / 6][(2 * i) % 6], B[(2 * i + 1) / 6][(2 * i + 1) % 6]);
+}
+
+UVS_DEV void load6(const double* p, double (&v)[6]) {
+    const double2* p2 = reinterpret_cast<const double2*>(p);
+#pragma unroll
+    for (int i = 0; i < 3; ++i) { const double2 t = p2[i]; v[2 * i] = t.x; v[2 * i + 1] = t.y; }
+}
+
+// ---- P0 / P in and out --------------------------------------------------------------------------
+// global P layouts: UVS_P_DENSE [N,N], UVS_P_BLOCKS [M,6,6]; src == nullptr -> identity
+template <int M>
+UVS_DEV void load_P(double* Ps, const double* src, int layout, int lane) {
+    constexpr int N = 6 * M, NB = M * (M + 1) / 2;
+    for (int e = lane; e < NB * 36; e += 32) {
+        const int b = e / 36, rc = e % 36, r = rc / 6, c = rc % 6;
+        int bi = 0;
+        while ((bi + 1) * (bi + 2) / 2 <= b) ++bi;
+        const int bj = b - bi * (bi + 1) / 2;
+        double v;
+        if (src == nullptr) v = (bi == bj && r == c) ? 1.0 : 0.0;
+        else if (layout == UVS_P_DENSE) {
+            // symmetrise the diagonal blocks from the lower triangle
+            const int gi = 6 * bi + r, gj = 6 * bj + c;
+            v = (gi >= gj) ? src[(size_t)gi * N + gj] : src[(size_t)gj * N + gi];
+        } else {
+            v = (bi == bj) ? ((r >= c) ? src[bi * 36 + r * 6 + c] : src[bi * 36 + c * 6 + r]) : 0.0;
+        }
+        Ps[b * kBlkStride + rc] = v;
+    }
+}
+
+template <int M>
+UVS_DEV void store_P(const double* Ps, double* dst, int layout, int lane) {
+    constexpr int N = 6 * M;
+    if (layout == UVS_P_DENSE) {
+        for (int e = lane; e < N * N; e += 32) {
+            const int gi = e / N, gj = e % N;
+            const int hi = gi >= gj ? gi : gj, lo = gi >= gj ? gj : gi;
+            const int bi = hi / 6, bj = lo / 6;
+            const int r = hi % 6, c = lo % 6;
+            dst[e] = Ps[blk_index(bi, bj) * kBlkStride + r * 6 + c];
+        }
+    } else {
+        for (int e = lane; e < M * 36; e += 32) {
+            const int d = e / 36;
+            dst[e] = Ps[blk_index(d, d) * kBlkStride + e % 36];
+        }
+    }
+}
+
+// ---- phase 1: P <- P + Q ;  At <- (P H^T)^T ------------------------------------------------------
+template <int M>
+UVS_DEV void predict_and_A(double* Ps, double* At, const double (&h)[6], const double* Qg, int q_identity,
+                           int lane) {
+    constexpr int N = 6 * M, NOFF = M * (M - 1) / 2;
+    if (lane < NOFF) {
+        int bi, bj;
+        offdiag_of_lane(lane, bi, bj);
+        double* pb = Ps + blk_index(bi, bj) * kBlkStride;
+        double B[6][6];
+        load_block(pb, B);
+        if (!q_identity) {
+#pragma unroll
+            for (int r = 0; r < 6; ++r)
+#pragma unroll
+                for (int c = 0; c < 6; ++c) B[r][c] += __ldg(Qg + (size_t)(6 * bi + r) * N + 6 * bj + c);
+            store_block(pb, B);
+        }
+        // rows 6bi.. of column bj, and (by symmetry) rows 6bj.. of column bi
+#pragma unroll
+        for (int r = 0; r < 6; ++r) {
+            double a = 0.0;
+#pragma unroll
+            for (int c = 0; c < 6; ++c) a += B[r][c] * h[c];
+            At[bj * N + 6 * bi + r] = a;
+        }
+#pragma unroll
+        for (int c = 0; c < 6; ++c) {
+            double a = 0.0;
+#pragma unroll
+            for (int r = 0; r < 6; ++r) a += B[r][c] * h[r];
+            At[bi * N + 6 * bj + c] = a;
+        }
+    }
+    for (int row = lane; row < N; row += 32) {
+        const int d = row / 6, r = row % 6;
+        double* pr = Ps + blk_index(d, d) * kBlkStride + r * 6;
+        double v[6];
+        load6(pr, v);
+        if (q_identity) {
+#pragma unroll
+            for (int c = 0; c < 6; ++c)
+                if (c == r) { v[c] += 1.0; pr[c] = v[c]; }
+        } else {
+#pragma unroll
+            for (int c = 0; c < 6; ++c) { v[c] += __ldg(Qg + (size_t)row * N + 6 * d + c); pr[c] = v[c]; }
+        }
+        double a = 0.0;
+#pragma unroll
+        for (int c = 0; c < 6; ++c) a += v[c] * h[c];
+        At[d * N + row] = a;
+    }
+}
+
+// ---- phase 5: P <- P - L1 R1^T (- L2 R2^T) on the lower blocks ------------------------------------
+// RANK2 = false: P -= Kt^T-rows x Ut^T-rows  (P[i][j] -= sum_k K[i][k] U[j][k])
+// RANK2 = true : P[i][j] -= sum_k K[i][k] V[j][k] + V[i][k] K[j][k]      (V held in Ut)
+template <int M, bool RANK2>
+UVS_DEV void rank_update(double* Ps, const double* Kt, const double* Ut, int lane) {
+    constexpr int N = 6 * M, NOFF = M * (M - 1) / 2;
+    if (lane < NOFF) {
+        int bi, bj;
+        offdiag_of_lane(lane, bi, bj);
+        double* pb = Ps + blk_index(bi, bj) * kBlkStride;
+        double B[6][6];
+        load_block(pb, B);
+#pragma unroll
+        for (int k = 0; k < M; ++k) {
+            double ki[6], uj[6];
+            load6(Kt + k * N + 6 * bi, ki);
+            load6(Ut + k * N + 6 * bj, uj);
+#pragma unroll
+            for (int r = 0; r < 6; ++r)
+#pragma unroll
+                for (int c = 0; c < 6; ++c) B[r][c] -= ki[r] * uj[c];
+            if (RANK2) {
+                double vi[6], kj[6];
+                load6(Ut + k * N + 6 * bi, vi);
+                load6(Kt + k * N + 6 * bj, kj);
+#pragma unroll
+                for (int r = 0; r < 6; ++r)
+#pragma unroll
+                    for (int c = 0; c < 6; ++c) B[r][c] -= vi[r] * kj[c];
+            }
+        }
+        store_block(pb, B);
+    }
+    // diagonal blocks: 4 lanes per block, lower triangle split 6/6/6/3, mirrored on store
+    {
+        const int d = lane >> 2, s = lane & 3;
+        if (d < M) {
+            const int rowA = 5 - s, nA = 6 - s;          // rows 5,4,3,2 with 6,5,4,3 entries
+            const int rowB = s - 1;                       // rows -,0,1,- with 0,1,2,0 entries
+            const int nB = (s == 1) ? 1 : ((s == 2) ? 2 : 0);
+            double* pb = Ps + blk_index(d, d) * kBlkStride;
+            const double* kt = Kt + 6 * d;
+            const double* ut = Ut + 6 * d;
+#pragma unroll
+            for (int e = 0; e < 6; ++e) {
+                const bool inA = e < nA;
+                const int row = inA ? rowA : rowB;
+                const int col = inA ? e : e - nA;
+                if (inA || (e - nA) < nB) {
+                    double acc = pb[row * 6 + col];
+#pragma unroll
+                    for (int k = 0; k < M; ++k) {
+                        acc -= kt[k * N + row] * ut[k * N + col];
+                        if (RANK2) acc -= ut[k * N + row] * kt[k * N + col];
+                    }
+                    pb[row * 6 + col] = acc;
+                    pb[col * 6 + row] = acc;
+                }
+            }
+        }
+    }
+}
+
+// ---- MCKF helpers: block Cholesky of P and the products with it ---------------------------------
+// Lp <- chol(P) in block layout; diagonal blocks hold the 6x6 factor (lower, TRUE diagonal, upper
+// part zeroed).  Returns false if P is not numerically SPD.
+template <int M>
+UVS_DEV bool block_cholesky(const double* Ps, double* Lp, int lane) {
+    constexpr int NB = M * (M + 1) / 2;
+    for (int e = lane; e < NB * kBlkStride; e += 32) Lp[e] = Ps[e];
+    __syncwarp();
+    bool ok = true;
+    for (int bj = 0; bj < M; ++bj) {
+        // (1) factor the diagonal block redundantly in registers
+        double Ld[21];
+        {
+            const double* pd = Lp + blk_index(bj, bj) * kBlkStride;
+#pragma unroll
+            for (int i = 0; i < 6; ++i)
+#pragma unroll
+                for (int j = 0; j <= i; ++j) Ld[tri(i, j)] = pd[i * 6 + j];
+        }
+        ok = chol_packed<6>(Ld) && ok;          // reciprocal diagonal
+        __syncwarp();
+        for (int e = lane; e < 36; e += 32) {
+            double* pd = Lp + blk_index(bj, bj) * kBlkStride;
+            const int i = e / 6, j = e % 6;
+            double v = 0.0;
+#pragma unroll
+            for (int a = 0; a < 6; ++a)
+#pragma unroll
+                for (int b = 0; b <= a; ++b)
+                    if (a == i && b == j) v = (a == b) ? 1.0 / Ld[tri(a, b)] : Ld[tri(a, b)];
+            pd[e] = v;
+        }
+        // (2) panel: rows of the blocks below, x <- x L_jj^-T  (forward substitution per row)
+        for (int rr = lane; rr < (M - 1 - bj) * 6; rr += 32) {
+            const int bi = bj + 1 + rr / 6, r = rr % 6;
+            double* pr = Lp + blk_index(bi, bj) * kBlkStride + r * 6;
+            double x[6];
+            load6(pr, x);
+            chol_forward<6>(Ld, x);
+#pragma unroll
+            for (int c = 0; c < 6; ++c) pr[c] = x[c];
+        }
+        __syncwarp();
+        // (3) trailing update: B_ik -= B_ij B_kj^T for bj < bk <= bi
+        const int nt = (M - 1 - bj) * (M - bj) / 2;
+        if (lane < nt) {
+            int ti = 0;
+            while ((ti + 1) * (ti + 2) / 2 <= lane) ++ti;
+            const int tk = lane - ti * (ti + 1) / 2;
+            const int bi = bj + 1 + ti, bk = bj + 1 + tk;
+            double C[6][6];
+            const double* pi = Lp + blk_index(bi, bj) * kBlkStride;
+            const double* pk = Lp + blk_index(bk, bj) * kBlkStride;
+            double* pc = Lp + blk_index(bi, bk) * kBlkStride;
+            load_block(pc, C);
+#pragma unroll
+            for (int k = 0; k < 6; ++k) {
+                double ci[6], ck[6];
+#pragma unroll
+                for (int r = 0; r < 6; ++r) { ci[r] = pi[r * 6 + k]; ck[r] = pk[r * 6 + k]; }
+#pragma unroll
+                for (int r = 0; r < 6; ++r)
+#pragma unroll
+                    for (int c = 0; c < 6; ++c) C[r][c] -= ci[r] * ck[c];
+            }
+            store_block(pc, C);
+        }
+        __syncwarp();
+    }
+    return ok;
+}
+
+// y <- Bp^-1 y  (block forward substitution, y in shared memory, length N)
+template <int M>
+UVS_DEV void block_forward(const double* Lp, double* y, int lane) {
+    constexpr int N = 6 * M;
+    for (int bj = 0; bj < M; ++bj) {
+        const double* pd = Lp + blk_index(bj, bj) * kBlkStride;
+        double yj[6];
+#pragma unroll
+        for (int i = 0; i < 6; ++i) {
+            double s = y[6 * bj + i];
+#pragma unroll
+            for (int k = 0; k < i; ++k) s -= pd[i * 6 + k] * yj[k];
+            yj[i] = s / pd[i * 6 + i];
+        }
+        __syncwarp();
+#pragma unroll
+        for (int i = 0; i < 6; ++i)
+            if (lane == i) y[6 * bj + i] = yj[i];
+        for (int row = 6 * (bj + 1) + lane; row < N; row += 32) {
+            const double* pr = Lp + blk_index(row / 6, bj) * kBlkStride + (row % 6) * 6;
+            double s = y[row];
+#pragma unroll
+            for (int k = 0; k < 6; ++k) s -= pr[k] * yj[k];
+            y[row] = s;
+        }
+        __syncwarp();
+    }
+}
+
+// Ahat^T (into Kt) <- (Bp diag(icx) Bp^T H^T)^T ; T1^T staged in Ut.  icx[j] = 1/cx_j.
+template <int M>
+UVS_DEV void mckf_weighted_A(const double* Lp, const double* icx, const double (&h)[6], double* T1t,
+                             double* Ahat_t, int lane) {
+    constexpr int N = 6 * M, NB = M * (M + 1) / 2;
+    for (int e = lane; e < M * N; e += 32) T1t[e] = 0.0;
+    __syncwarp();
+    // T1[6bj+c][k] = icx * sum_r Lp[6k+r][6bj+c] h_r   over blocks (k, bj), bj <= k
+    for (int b = lane; b < NB; b += 32) {
+        int k = 0;
+        while ((k + 1) * (k + 2) / 2 <= b) ++k;
+        const int bj = b - k * (k + 1) / 2;
+        double B[6][6];
+        load_block(Lp + b * kBlkStride, B);        // diagonal blocks have their upper part zeroed
+#pragma unroll
+        for (int c = 0; c < 6; ++c) {
+            double s = 0.0;
+#pragma unroll
+            for (int r = 0; r < 6; ++r) s += B[r][c] * h[r];
+            T1t[k * N + 6 * bj + c] = s * icx[6 * bj + c];
+        }
+    }
+    __syncwarp();
+    // Ahat[6bi+r][k] = sum_{bj <= min(bi,k)} sum_c Lp[6bi+r][6bj+c] T1[6bj+c][k]
+    for (int e = lane; e < M * M; e += 32) {
+        const int bi = e / M, k = e % M;
+        double acc[6] = {0, 0, 0, 0, 0, 0};
+        const int lim = bi < k ? bi : k;
+        for (int bj = 0; bj <= lim; ++bj) {
+            double B[6][6], t[6];
+            load_block(Lp + blk_index(bi, bj) * kBlkStride, B);
+            load6(T1t + k * N + 6 * bj, t);
+#pragma unroll
+            for (int r = 0; r < 6; ++r)
+#pragma unroll
+                for (int c = 0; c < 6; ++c) acc[r] += B[r][c] * t[c];
+        }
+#pragma unroll
+        for (int r = 0; r < 6; ++r) Ahat_t[k * N + 6 * bi + r] = acc[r];
+    }
+    __syncwarp();
+}
+
+// ---- S = s0_scale * H Ain + Rh, factorised redundantly in every lane's registers ------------------
+// Ain: A^T-like array (M x N).  w_lane: lane i < M carries the i-th diagonal weight of W, where
+// Rh = Br W Br^T (plain_R: Rh = R).  Optionally stores S0 = H Ain (S0sm) and the matrix D used by
+// U = A + Kp D:  d_mode 1 -> D = Rh - R,  d_mode 2 -> D = dscale * R.
+template <int M>
+UVS_DEV bool build_and_factor_S(const double* Ain, const double (&h)[6], const DenseConsts<M>& cc,
+                                double w_lane, bool plain_R, double s0_scale, double* Ssm, double* wsm,
+                                double* Dsm, int d_mode, double dscale,
+                                double (&L)[M * (M + 1) / 2], int lane) {
+    constexpr int N = 6 * M;
+    if (lane < M) wsm[lane] = w_lane;
+    __syncwarp();
+    for (int e = lane; e < M * M; e += 32) {
+        const int i = e / M, k = e % M;
+        double s0 = 0.0;
+#pragma unroll
+        for (int r = 0; r < 6; ++r) s0 += h[r] * Ain[k * N + 6 * i + r];
+        double rh;
+        if (plain_R) rh = cc.R[e];
+        else if (cc.r_identity) rh = (i == k) ? wsm[i] : 0.0;
+        else {
+            rh = 0.0;
+#pragma unroll
+            for (int j = 0; j < M; ++j) rh += cc.Br[i * M + j] * wsm[j] * cc.Br[k * M + j];
+        }
+        Ssm[e] = s0_scale * s0 + rh;
+        if (d_mode == 1) Dsm[e] = rh - cc.R[e];
+        else if (d_mode == 2) Dsm[e] = dscale * cc.R[e];
+    }
+    __syncwarp();
+#pragma unroll
+    for (int i = 0; i < M; ++i)
+#pragma unroll
+        for (int j = 0; j <= i; ++j) L[tri(i, j)] = Ssm[i * M + j];
+    return chol_packed<M>(L);
+}
+
+struct StepOut {
+    int flags = 0;
+    int epoch = 0;
+};
+
+// One predict + update of the filter held in `w`.  z_lane: Z_i on lane i < M.  Returns kappa_i on
+// lane i < M (experiment.py:306-308).  K^T is left in w.Kt.
+template <int M, int METHOD>
+UVS_DEV double dense_step(DenseWS<M, METHOD == UVS_METHOD_MCKF>& w, const DenseConsts<M>& cc,
+                          const uvs_filter_params& fp, const double (&h)[6], double z_lane, double sigma,
+                          int lane, StepOut& out) {
+    constexpr int N = 6 * M;
+    predict_and_A<M>(w.P, w.At, h, fp.Q, cc.q_identity, lane);
+    __syncwarp();
+
+    // innovation nu = Z - H X, gathered on every lane
+    double nu_l = 0.0;
+    if (lane < M) {
+        nu_l = z_lane;
+#pragma unroll
+        for (int r = 0; r < 6; ++r) nu_l -= h[r] * w.X[6 * lane + r];
+    }
+    double nu[M];
+#pragma unroll
+    for (int j = 0; j < M; ++j) nu[j] = shfl_d(nu_l, j);
+    // whitened innovation e = Br^-1 nu
+    double e_l = 0.0;
+    if (lane < M) {
+        if (cc.r_identity) e_l = nu_l;
+        else {
+#pragma unroll
+            for (int j = 0; j < M; ++j) e_l += cc.Brinv[lane * M + j] * nu[j];
+        }
+    }
+    double kappa = 1.0;
+    double L[M * (M + 1) / 2];
+
+    if (METHOD != UVS_METHOD_MCKF) {
+        double gain_scale = 1.0, dscale = 0.0;
+        bool plain_R = true;
+        double s0_scale = 1.0, w_lane = 1.0;
+        int d_mode = 0;
+        if (METHOD == UVS_METHOD_GMCKF) {
+            const double c = (lane < M) ? gaussian_kernel(e_l, sigma) : 1.0;      // experiment.py:274-276
+            kappa = c;
+            w_lane = 1.0 / (c + 1e-6);                                             // experiment.py:280
+            plain_R = false;
+            d_mode = fp.joseph ? 1 : 0;
+        } else if (METHOD == UVS_METHOD_IMCCKF) {
+            double q = 0.0;                                                        // experiment.py:258-261
+#pragma unroll
+            for (int j = 0; j < M; ++j) { const double ej = shfl_d(e_l, j); q += ej * ej; }
+            const double c = gaussian_kernel(sqrt(q), sigma);
+            s0_scale = c; gain_scale = c; dscale = 1.0 - c;
+            d_mode = fp.joseph ? 2 : 0;
+        }
+        const bool ok = build_and_factor_S<M>(w.At, h, cc, w_lane, plain_R, s0_scale, w.S, w.ib, w.D, d_mode,
+                                              dscale, L, lane);
+        if (!ok) {                       // S not SPD: skip the correction, P keeps +Q
+            out.flags |= UVS_FLAG_NOT_SPD;
+            for (int e = lane; e < M * N; e += 32) w.Kt[e] = 0.0;
+            __syncwarp();
+            return kappa;
+        }
+        const bool use_D = d_mode != 0;
+        for (int row = lane; row < N; row += 32) {
+            double a[M], x[M];
+#pragma unroll
+            for (int k = 0; k < M; ++k) { a[k] = w.At[k * N + row]; x[k] = a[k]; }
+            chol_solve<M>(L, x);                                  // Kp row = A row S^-1
+            double dxr = 0.0;
+#pragma unroll
+            for (int k = 0; k < M; ++k) {
+                w.Kt[k * N + row] = gain_scale * x[k];
+                dxr += gain_scale * x[k] * nu[k];
+            }
+            w.X[row] += dxr;                                     // experiment.py:193 / 265 / 291
+#pragma unroll
+            for (int k = 0; k < M; ++k) {
+                double u = a[k];
+                if (use_D) {
+#pragma unroll
+                    for (int j = 0; j < M; ++j) u += x[j] * w.D[j * M + k];
+                }
+                w.Ut[k * N + row] = u;
+            }
+        }
+        __syncwarp();
+        rank_update<M, false>(w.P, w.Kt, w.Ut, lane);
+        __syncwarp();
+        return kappa;
+    } else {
+        // ------------------------------------------------------------------ MCKF (experiment.py:194-250)
+        // S0 of the TRUE predicted covariance is needed by the Joseph form
+        for (int e = lane; e < M * M; e += 32) {
+            const int i = e / M, k = e % M;
+            double s0 = 0.0;
+#pragma unroll
+            for (int r = 0; r < 6; ++r) s0 += h[r] * w.At[k * N + 6 * i + r];
+            w.D[e] = s0;
+        }
+        const bool spd = block_cholesky<M>(w.P, w.Lp, lane);
+        for (int row = lane; row < N; row += 32) w.Xc[row] = w.X[row];
+        __syncwarp();
+        if (!spd) {
+            out.flags |= UVS_FLAG_NOT_SPD;
+            return kappa;
+        }
+        bool skip = false;
+        int epoch = 0;
+        double difference = INFINITY;
+        while (difference > fp.fpi_threshold && epoch < fp.fpi_epoch_max) {
+            const double* Ain = w.At;
+            if (epoch > 0) {
+                // ex = Bp^-1 (X - Xc) ; cx = G(ex)
+                for (int row = lane; row < N; row += 32) w.dx[row] = w.X[row] - w.Xc[row];
+                __syncwarp();
+                block_forward<M>(w.Lp, w.dx, lane);
+                bool cx_zero = false;
+                for (int row = lane; row < N; row += 32) {
+                    const double cx = gaussian_kernel(w.dx[row], sigma);
+                    cx_zero = cx_zero || (cx == 0.0);
+                    w.dx[row] = 1.0 / cx;
+                }
+                cx_zero = __any_sync(UVS_FULL_MASK, cx_zero);
+                __syncwarp();
+                if (cx_zero) { out.flags |= UVS_FLAG_CX_SINGULAR; skip = true; break; }
+                mckf_weighted_A<M>(w.Lp, w.dx, h, w.Ut, w.Kt, lane);
+                Ain = w.Kt;
+            }
+            // ey = Br^-1 (Z - H Xc) ; cy = G(ey)
+            double r_l = 0.0;
+            if (lane < M) {
+                r_l = z_lane;
+#pragma unroll
+                for (int r = 0; r < 6; ++r) r_l -= h[r] * w.Xc[6 * lane + r];
+            }
+            double ey = 0.0;
+            if (cc.r_identity) ey = r_l;
+            else {
+#pragma unroll
+                for (int j = 0; j < M; ++j) { const double rj = shfl_d(r_l, j); if (lane < M) ey += cc.Brinv[lane * M + j] * rj; }
+            }
+            const double cy = (lane < M) ? gaussian_kernel(ey, sigma) : 1.0;
+            if (__any_sync(UVS_FULL_MASK, cy == 0.0)) {                 // experiment.py:231-236
+                out.flags |= UVS_FLAG_SKIP_SINGULAR; skip = true; break;
+            }
+            const bool ok = build_and_factor_S<M>(Ain, h, cc, 1.0 / cy, false, 1.0, w.S, w.ib, nullptr, 0, 0.0, L, lane);
+            if (!ok) { out.flags |= UVS_FLAG_NOT_SPD; skip = true; break; }
+            // K rows, X_corrected = X + K (Z - H X)        experiment.py:238-242
+            double num = 0.0, den = 0.0;
+            for (int row = lane; row < N; row += 32) {
+                double x[M];
+#pragma unroll
+                for (int k = 0; k < M; ++k) x[k] = Ain[k * N + row];
+                chol_solve<M>(L, x);
+                double xc = w.X[row];
+#pragma unroll
+                for (int k = 0; k < M; ++k) { w.Kt[k * N + row] = x[k]; xc += x[k] * nu[k]; }
+                const double old = w.Xc[row];
+                num += (xc - old) * (xc - old);
+                den += old * old;
+                w.Xc[row] = xc;
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) { num += shfl_xor_d(num, o); den += shfl_xor_d(den, o); }
+            difference = sqrt(num) / sqrt(den);                        // experiment.py:244
+            ++epoch;
+            __syncwarp();
+            if (epoch == fp.fpi_epoch_max && fp.mckf_skip) {           // experiment.py:246-248
+                out.flags |= UVS_FLAG_SKIP_MAXEPOCH; skip = true;
+            }
+        }
+        out.epoch = epoch;
+        if (skip) return kappa;
+        // X = X_corrected ; Joseph with the last K:  V = A - K (S0 + R)/2
+        for (int row = lane; row < N; row += 32) {
+            w.X[row] = w.Xc[row];
+            double kr[M];
+#pragma unroll
+            for (int k = 0; k < M; ++k) kr[k] = w.Kt[k * N + row];
+#pragma unroll
+            for (int k = 0; k < M; ++k) {
+                double v = w.At[k * N + row];
+#pragma unroll
+                for (int j = 0; j < M; ++j) v -= 0.5 * kr[j] * (w.D[j * M + k] + cc.R[j * M + k]);
+                w.Ut[k * N + row] = v;
+            }
+        }
+        __syncwarp();
+        rank_update<M, true>(w.P, w.Kt, w.Ut, lane);
+        __syncwarp();
+        return kappa;
+    }
+}
+
+// Fill the per-CTA constants (R, chol(R), its inverse) — experiment.py:76,121-122.  One thread.
+template <int M>
+__device__ void init_consts(DenseConsts<M>& cc, const uvs_filter_params& fp) {
+    bool ident = (fp.R == nullptr);
+    for (int i = 0; i < M; ++i)
+        for (int j = 0; j < M; ++j) cc.R[i * M + j] = fp.R ? fp.R[i * M + j] : (i == j ? 1.0 : 0.0);
+    if (!ident) {
+        ident = true;
+        for (int i = 0; i < M; ++i)
+            for (int j = 0; j < M; ++j) ident = ident && (cc.R[i * M + j] == (i == j ? 1.0 : 0.0));
+    }
+    cc.r_identity = ident;
+    cc.q_identity = (fp.Q == nullptr);
+    // Cholesky (lower) and inverse of the factor
+    for (int i = 0; i < M * M; ++i) { cc.Br[i] = 0.0; cc.Brinv[i] = 0.0; }
+    for (int j = 0; j < M; ++j) {
+        double d = cc.R[j * M + j];
+        for (int k = 0; k < j; ++k) d -= cc.Br[j * M + k] * cc.Br[j * M + k];
+        const double s = sqrt(d);
+        cc.Br[j * M + j] = s;
+        for (int i = j + 1; i < M; ++i) {
+            double v = cc.R[i * M + j];
+            for (int k = 0; k < j; ++k) v -= cc.Br[i * M + k] * cc.Br[j * M + k];
+            cc.Br[i * M + j] = v / s;
+        }
+    }
+    for (int c = 0; c < M; ++c)
+        for (int i = c; i < M; ++i) {
+            double v = (i == c) ? 1.0 : 0.0;
+            for (int k = c; k < i; ++k) v -= cc.Br[i * M + k] * cc.Brinv[k * M + c];
+            cc.Brinv[i * M + c] = v / cc.Br[i * M + i];
+        }
+}
+
+}  // namespace uvs

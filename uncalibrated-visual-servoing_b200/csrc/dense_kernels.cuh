@@ -1,0 +1,261 @@
+// dense_kernels.cuh — kernels of the dense (general SPD covariance) family: one filter per warp.
+//   dense_replay_kernel       uvs_filter_step / uvs_replay  (experiment.py:166-300, open loop)
+//   dense_closed_loop_kernel  uvs_closed_loop               (experiment.py:48-359, whole trial)
+// Instantiated per measurement count M in dense_m{2,6,8}.cu.
+#pragma once
+#include "dense.cuh"
+#include "kernel_args.cuh"
+
+namespace uvs {
+
+template <int M, bool MCKF>
+__host__ __device__ constexpr size_t dense_smem_bytes(int warps) {
+    return sizeof(DenseConsts<M>) + (size_t)warps * sizeof(DenseWS<M, MCKF>);
+}
+
+template <int M, int METHOD>
+__global__ void __launch_bounds__(320) dense_replay_kernel(const __grid_constant__ ReplayArgs a) {
+    constexpr int N = 6 * M;
+    constexpr bool MCKF = METHOD == UVS_METHOD_MCKF;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    DenseConsts<M>& cc = *reinterpret_cast<DenseConsts<M>*>(smem_raw);
+    DenseWS<M, MCKF>* wsv = reinterpret_cast<DenseWS<M, MCKF>*>(smem_raw + sizeof(DenseConsts<M>));
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpc = blockDim.x >> 5;
+    if (threadIdx.x == 0) init_consts<M>(cc, a.fp);
+    __syncthreads();
+    DenseWS<M, MCKF>& w = wsv[warp];
+    const size_t psz = (a.p_layout == UVS_P_DENSE) ? (size_t)N * N : (size_t)M * 36;
+
+    for (long long b = (long long)blockIdx.x * wpc + warp; b < a.B; b += (long long)gridDim.x * wpc) {
+        for (int r = lane; r < N; r += 32) w.X[r] = a.X[b * N + r];
+        load_P<M>(w.P, a.P ? a.P + b * psz : nullptr, a.p_layout, lane);
+        __syncwarp();
+        double f_prev = (!a.direct && lane < M) ? a.f_init[b * M + lane] : 0.0;
+        for (int k = 0; k < a.T; ++k) {
+            double h[6], z = 0.0, sigma;
+            if (a.direct) {
+#pragma unroll
+                for (int r = 0; r < 6; ++r) h[r] = a.h[b * 6 + r];
+                if (lane < M) z = a.Z[b * M + lane];
+                sigma = a.sigma;
+            } else {
+                if (lane < M) {
+                    const double fk = a.f[((size_t)b * a.T + k) * M + lane];
+                    z = fk - f_prev;                                    // experiment.py:170-177
+                    f_prev = fk;
+                }
+#pragma unroll
+                for (int r = 0; r < 6; ++r)                             // experiment.py:183-188
+                    h[r] = (k == 0) ? 0.0 : a.dq[((size_t)b * a.T + k - 1) * 6 + r];
+                sigma = annealed_bw(a.fp.kernel_bw, a.fp.annealing, k, a.k_max);
+            }
+            StepOut so;
+            const double kappa = dense_step<M, METHOD>(w, cc, a.fp, h, z, sigma, lane, so);
+            const size_t bt = (size_t)b * a.T + k;
+            if (a.X_out) for (int r = lane; r < N; r += 32) a.X_out[bt * N + r] = w.X[r];
+            if (a.P_out) store_P<M>(w.P, a.P_out + bt * psz, a.p_layout, lane);
+            if (a.kappa_out && lane < M) a.kappa_out[bt * M + lane] = kappa;
+            if (a.flags_out && lane == 0) a.flags_out[bt] = so.flags | (so.epoch << UVS_FLAG_EPOCH_SHIFT);
+            if (a.K_out) for (int e = lane; e < N * M; e += 32) a.K_out[bt * N * M + e] = w.Kt[(e % M) * N + e / M];
+            __syncwarp();
+        }
+        for (int r = lane; r < N; r += 32) a.X[b * N + r] = w.X[r];
+        if (a.P) store_P<M>(w.P, a.P + b * psz, a.p_layout, lane);
+        __syncwarp();
+    }
+}
+
+template <int M, int METHOD>
+__global__ void __launch_bounds__(320) dense_closed_loop_kernel(const __grid_constant__ ClosedLoopArgs a) {
+    constexpr int N = 6 * M;
+    constexpr bool MCKF = METHOD == UVS_METHOD_MCKF;
+    constexpr int LOGW = 6 + 2 * M;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    DenseConsts<M>& cc = *reinterpret_cast<DenseConsts<M>*>(smem_raw);
+    DenseWS<M, MCKF>* wsv = reinterpret_cast<DenseWS<M, MCKF>*>(smem_raw + sizeof(DenseConsts<M>));
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpc = blockDim.x >> 5;
+    const uvs_closed_loop_cfg& cfg = a.cfg;
+    if (threadIdx.x == 0) init_consts<M>(cc, cfg.filt);
+    __syncthreads();
+    DenseWS<M, MCKF>& w = wsv[warp];
+    const int T = cfg.T;
+
+    for (long long b = (long long)blockIdx.x * wpc + warp; b < a.B; b += (long long)gridDim.x * wpc) {
+        const uint64_t trial = a.trial0 + (uint64_t)b;
+        // noise level of this trial (main.py:121-127)
+        double rho = cfg.noise.rho, alpha = cfg.noise.alpha;
+        if (cfg.sweep_len > 0 && cfg.sweep_param != 0) {
+            long long lvl = (long long)(trial / (uint64_t)(cfg.sweep_epoch > 0 ? cfg.sweep_epoch : 1));
+            if (lvl >= cfg.sweep_len) lvl = cfg.sweep_len - 1;
+            if (cfg.sweep_param == 1) rho = cfg.sweep[lvl]; else alpha = cfg.sweep[lvl];
+        }
+        double q[6];
+        if (a.io.q0_in) {
+#pragma unroll
+            for (int j = 0; j < 6; ++j) q[j] = a.io.q0_in[b * 6 + j];
+        } else start_pose(cfg, trial, q);
+
+        // ---- initial state (experiment.py:70-117) ---------------------------------------------
+        double f_l = 0.0;              // this lane's feature coordinate (noisy, as logged)
+        {
+            UR10 kin;
+            Tf T6;
+            ur10_fk(q, T6, &kin);
+            double zc = 1.0, u = 0.0, v = 0.0, depth;
+            if (lane < M) {
+                const double* pw = cfg.targets + 3 * (lane >> 1);
+                u = project_coord(T6, pw, 0, depth);
+                v = project_coord(T6, pw, 1, depth);
+                zc = camera_distance(T6, pw);
+            }
+            if (a.io.X0_in) {
+                for (int r = lane; r < N; r += 32) w.X[r] = a.io.X0_in[b * N + r];
+                if (cfg.initial_guess && lane < M) f_l = (lane & 1) ? v : u;
+            } else if (cfg.initial_guess) {
+                double Jg[6][6];
+                ur10_jacobian(kin, Jg);
+                if (lane < M) {
+                    double row[6];
+                    initial_guess_row(kin, Jg, lane, u, v, zc, row);
+#pragma unroll
+                    for (int j = 0; j < 6; ++j) w.X[6 * lane + j] = row[j];
+                    f_l = (lane & 1) ? v : u;
+                }
+            } else {
+                for (int r = lane; r < N; r += 32) {                    // experiment.py:117
+                    double ua, ub;
+                    uniforms(cfg.noise.seed, trial, 0, (uint32_t)r, 0, PURPOSE_X0, ua, ub);
+                    w.X[r] = ua;
+                }
+            }
+        }
+        load_P<M>(w.P, cfg.P0, UVS_P_DENSE, lane);
+        __syncwarp();
+
+        HoldState hs;
+        double ise = 0.0, iae = 0.0, itae = 0.0;
+        double dq[6] = {0, 0, 0, 0, 0, 0};
+        int status = UVS_STATUS_SUCCESS, frames = 0, flags_all = 0;
+        const double desired = (lane < M) ? cfg.desired_f[lane] : 0.0;
+
+        for (int k = 0; k < T; ++k) {
+            const double t = (double)(k + 1) * cfg.dt;
+            Tf T6;
+            ur10_fk(q, T6);
+            double f_true = 0.0, depth = 1.0;
+            if (lane < M) f_true = project_coord(T6, cfg.targets + 3 * (lane >> 1), lane & 1, depth);
+            if (cfg.fov_check) {
+                const bool bad = (lane < M) && !(f_true >= 0.0 && f_true < kResolution && depth > kMinDepth);
+                if (__any_sync(UVS_FULL_MASK, bad)) {                   // NaN centroid -> FAIL
+                    status = UVS_STATUS_FAIL; flags_all |= UVS_FLAG_OUT_OF_VIEW; break;
+                }
+            }
+            double nz;
+            if (a.io.noise_in) nz = (lane < M) ? a.io.noise_in[((size_t)b * T + k) * M + lane] : 0.0;
+            else if (cfg.noise.type == UVS_NOISE_NONE) nz = 0.0;
+            else nz = next_noise(hs, cfg.noise, rho, alpha, trial, (uint32_t)k, lane, M);
+            const double f_new = f_true + nz;                            // experiment.py:130-135
+            const double z = f_new - f_l;                                // experiment.py:170-177
+            f_l = f_new;
+            double h[6];
+#pragma unroll
+            for (int r = 0; r < 6; ++r) h[r] = (k == 0) ? 0.0 : dq[r];   // experiment.py:183-188
+            const double sigma = annealed_bw(cfg.filt.kernel_bw, cfg.filt.annealing, k, T);
+            StepOut so;
+            const double kappa = dense_step<M, METHOD>(w, cc, cfg.filt, h, z, sigma, lane, so);
+            flags_all |= so.flags;
+
+            // IBVS: dq = -gain pinv(J) (kappa o error)                    experiment.py:300-312
+            const double err = f_l - desired;
+            double x[6];
+            int ib_flags = 0;
+            pinv_warp<M>(w.X, kappa * err, w.ib, lane, x, ib_flags);
+            flags_all |= ib_flags;
+            bool bad = false;
+#pragma unroll
+            for (int r = 0; r < 6; ++r) { dq[r] = -cfg.ibvs_gain * x[r]; bad = bad || !isfinite(dq[r]); }
+            for (int r = lane; r < N; r += 32) bad = bad || !isfinite(w.X[r]);
+            if (__any_sync(UVS_FULL_MASK, bad)) {                        // experiment.py:313-316
+                status = UVS_STATUS_FAIL; flags_all |= UVS_FLAG_NONFINITE; break;
+            }
+            // logging (experiment.py:323-331) and error integrals (plot_errorbar.m:39-84)
+            if (a.io.log) {
+                double* lg = a.io.log + ((size_t)b * T + k) * LOGW;
+#pragma unroll
+                for (int r = 0; r < 6; ++r) if (lane == r) lg[r] = q[r];
+                if (lane < M) { lg[6 + lane] = f_l; lg[6 + M + lane] = nz; }
+            }
+            if (lane < M) {
+                const double e = desired - f_l;
+                ise += e * e; iae += fabs(e); itae += t * fabs(e);
+            }
+            ++frames;
+#pragma unroll
+            for (int r = 0; r < 6; ++r) q[r] += dq[r] * cfg.dt;          // experiment.py:320,335
+        }
+        // ||.||_2 over the M coordinates
+        double s0 = ise * ise, s1 = iae * iae, s2 = itae * itae;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) { s0 += shfl_xor_d(s0, o); s1 += shfl_xor_d(s1, o); s2 += shfl_xor_d(s2, o); }
+        if (lane == 0) {
+            a.io.stats[b * 3 + 0] = sqrt(s0);
+            a.io.stats[b * 3 + 1] = sqrt(s1);
+            a.io.stats[b * 3 + 2] = sqrt(s2);
+            a.io.status[b] = status;
+            if (a.io.frames) a.io.frames[b] = frames;
+            if (a.io.flags) a.io.flags[b] = flags_all;
+        }
+        if (a.io.X_out) for (int r = lane; r < N; r += 32) a.io.X_out[b * N + r] = w.X[r];
+        if (a.io.P_out) {
+            const size_t psz = (a.io.p_layout == UVS_P_DENSE) ? (size_t)N * N : (size_t)M * 36;
+            store_P<M>(w.P, a.io.P_out + b * psz, a.io.p_layout, lane);
+        }
+        __syncwarp();
+    }
+}
+
+// host-side dispatch (defined once per M in dense_m*.cu)
+template <int M> cudaError_t launch_dense_replay(const ReplayArgs& a, int grid, int block, cudaStream_t st);
+template <int M> cudaError_t launch_dense_closed_loop(const ClosedLoopArgs& a, int grid, int block, cudaStream_t st);
+template <int M> size_t dense_ws_bytes(int method, int warps);
+
+#define UVS_DEFINE_DENSE_LAUNCHERS(MM)                                                                       \
+    template <> size_t dense_ws_bytes<MM>(int method, int warps) {                                           \
+        return method == UVS_METHOD_MCKF ? dense_smem_bytes<MM, true>(warps) : dense_smem_bytes<MM, false>(warps); \
+    }                                                                                                        \
+    template <int METHOD> static cudaError_t replay_one_##MM(const ReplayArgs& a, int grid, int block, cudaStream_t st) { \
+        const size_t smem = dense_ws_bytes<MM>(METHOD, block / 32);                                          \
+        cudaError_t e = cudaFuncSetAttribute(dense_replay_kernel<MM, METHOD>,                                \
+                                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);        \
+        if (e != cudaSuccess) return e;                                                                      \
+        dense_replay_kernel<MM, METHOD><<<grid, block, smem, st>>>(a);                                       \
+        return cudaGetLastError();                                                                           \
+    }                                                                                                        \
+    template <int METHOD> static cudaError_t closed_one_##MM(const ClosedLoopArgs& a, int grid, int block, cudaStream_t st) { \
+        const size_t smem = dense_ws_bytes<MM>(METHOD, block / 32);                                          \
+        cudaError_t e = cudaFuncSetAttribute(dense_closed_loop_kernel<MM, METHOD>,                           \
+                                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);        \
+        if (e != cudaSuccess) return e;                                                                      \
+        dense_closed_loop_kernel<MM, METHOD><<<grid, block, smem, st>>>(a);                                  \
+        return cudaGetLastError();                                                                           \
+    }                                                                                                        \
+    template <> cudaError_t launch_dense_replay<MM>(const ReplayArgs& a, int grid, int block, cudaStream_t st) { \
+        switch (a.fp.method) {                                                                               \
+        case UVS_METHOD_KF: return replay_one_##MM<UVS_METHOD_KF>(a, grid, block, st);                       \
+        case UVS_METHOD_MCKF: return replay_one_##MM<UVS_METHOD_MCKF>(a, grid, block, st);                   \
+        case UVS_METHOD_IMCCKF: return replay_one_##MM<UVS_METHOD_IMCCKF>(a, grid, block, st);               \
+        case UVS_METHOD_GMCKF: return replay_one_##MM<UVS_METHOD_GMCKF>(a, grid, block, st);                 \
+        default: return cudaErrorInvalidValue;                                                               \
+        }                                                                                                    \
+    }                                                                                                        \
+    template <> cudaError_t launch_dense_closed_loop<MM>(const ClosedLoopArgs& a, int grid, int block, cudaStream_t st) { \
+        switch (a.cfg.filt.method) {                                                                         \
+        case UVS_METHOD_KF: return closed_one_##MM<UVS_METHOD_KF>(a, grid, block, st);                       \
+        case UVS_METHOD_MCKF: return closed_one_##MM<UVS_METHOD_MCKF>(a, grid, block, st);                   \
+        case UVS_METHOD_IMCCKF: return closed_one_##MM<UVS_METHOD_IMCCKF>(a, grid, block, st);               \
+        case UVS_METHOD_GMCKF: return closed_one_##MM<UVS_METHOD_GMCKF>(a, grid, block, st);                 \
+        default: return cudaErrorInvalidValue;                                                               \
+        }                                                                                                    \
+    }
+
+}  // namespace uvs

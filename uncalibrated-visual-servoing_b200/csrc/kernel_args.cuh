@@ -1,0 +1,64 @@
+// kernel_args.cuh — argument blocks and per-trial helpers shared by the dense and the
+// block-diagonal kernel families.
+#pragma once
+#include "common.cuh"
+#include "philox.cuh"
+#include "ur10.cuh"
+
+namespace uvs {
+
+struct ReplayArgs {
+    uvs_filter_params fp;
+    long long B;
+    int T, k_max, direct, p_layout;
+    double sigma;
+    const double *f, *dq, *f_init;     // replay inputs
+    const double *h, *Z;               // direct (single step) inputs
+    double *X, *P;                     // in/out state
+    double *X_out, *P_out, *kappa_out, *K_out;
+    int32_t* flags_out;
+};
+
+struct ClosedLoopArgs {
+    uvs_closed_loop_cfg cfg;
+    uvs_closed_loop_io io;
+    unsigned long long trial0;
+    long long B;
+};
+
+// noise of this frame for coordinate `lane` with the pair hold of noise.py:81-118
+UVS_DEV double next_noise(HoldState& hs, const uvs_noise_params& np, double rho, double alpha, uint64_t trial,
+                          uint32_t frame, int lane, int M) {
+    bool redraw = false;
+    double fresh = 0.0;
+    if (lane < M) {
+        if (hs.cnt >= hs.cnt_max) {
+            hs.cnt = 0;
+            redraw = true;
+            fresh = noise_sample(np, rho, alpha, trial, frame, (uint32_t)lane);
+        } else {
+            hs.cnt += 1;
+        }
+    }
+    const bool outl = redraw && (fabs(fresh) > 20.0);
+    const bool pair = outl || __shfl_xor_sync(UVS_FULL_MASK, outl, 1);
+    if (redraw) {
+        hs.cnt_max = pair ? np.hold_cnt : 0;
+        hs.cur = fresh;
+    }
+    return hs.cur;
+}
+
+UVS_DEV void start_pose(const uvs_closed_loop_cfg& cfg, uint64_t trial, double (&q)[6]) {
+#pragma unroll
+    for (int j = 0; j < 6; ++j) q[j] = cfg.q_start[j];
+    if (cfg.change_q_start) {                                   // main.py:129-134
+        double r0, r1, dummy;
+        uniforms(cfg.pose_seed, trial, 0, 0, 0, PURPOSE_POSE, r0, dummy);
+        uniforms(cfg.pose_seed, trial, 0, 1, 0, PURPOSE_POSE, r1, dummy);
+        q[0] = cfg.q_start[0] + 2 * (r0 - 1) * (M_PI / 18);
+        q[1] = cfg.q_start[1] + 2 * (r1 - 1) * (M_PI / 9);
+    }
+}
+
+}  // namespace uvs

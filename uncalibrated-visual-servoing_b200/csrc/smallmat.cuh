@@ -1,0 +1,280 @@
+// smallmat.cuh — register-resident small dense solves (fully unrolled, one thread).
+// Used redundantly by every lane of a warp where a filter needs an m x m (m <= 8)
+// factorisation: cheaper than a shuffle/smem-cooperative factorisation at this size
+// because it needs no synchronisation and its ~8 dependent rsqrt steps overlap with
+// other warps' DFMA streams.
+#pragma once
+#include "common.cuh"
+
+namespace uvs {
+
+// packed lower-triangular index
+__host__ __device__ constexpr int tri(int i, int j) { return i * (i + 1) / 2 + j; }
+
+// In-place Cholesky of a packed lower SPD matrix held in registers.
+// On exit L holds the factor with its DIAGONAL REPLACED BY ITS RECIPROCAL.
+// Returns false when a pivot is not positive/finite (np.linalg.cholesky would raise).
+template <int M>
+UVS_DEV bool chol_packed(double (&L)[M * (M + 1) / 2]) {
+    bool ok = true;
+#pragma unroll
+    for (int j = 0; j < M; ++j) {
+        double d = L[tri(j, j)];
+#pragma unroll
+        for (int k = 0; k < j; ++k) d -= L[tri(j, k)] * L[tri(j, k)];
+        ok = ok && (d > 0.0) && isfinite(d);
+        const double inv = rsqrt(d);
+        L[tri(j, j)] = inv;
+#pragma unroll
+        for (int i = j + 1; i < M; ++i) {
+            double s = L[tri(i, j)];
+#pragma unroll
+            for (int k = 0; k < j; ++k) s -= L[tri(i, k)] * L[tri(j, k)];
+            L[tri(i, j)] = s * inv;
+        }
+    }
+    return ok;
+}
+
+// x <- (L L^T)^-1 x   with L from chol_packed (reciprocal diagonal)
+template <int M>
+UVS_DEV void chol_solve(const double (&L)[M * (M + 1) / 2], double (&x)[M]) {
+#pragma unroll
+    for (int j = 0; j < M; ++j) {
+        double s = x[j];
+#pragma unroll
+        for (int k = 0; k < j; ++k) s -= L[tri(j, k)] * x[k];
+        x[j] = s * L[tri(j, j)];
+    }
+#pragma unroll
+    for (int j = M - 1; j >= 0; --j) {
+        double s = x[j];
+#pragma unroll
+        for (int k = j + 1; k < M; ++k) s -= L[tri(k, j)] * x[k];
+        x[j] = s * L[tri(j, j)];
+    }
+}
+
+// y <- L^-1 y (forward substitution only)
+template <int M>
+UVS_DEV void chol_forward(const double (&L)[M * (M + 1) / 2], double (&x)[M]) {
+#pragma unroll
+    for (int j = 0; j < M; ++j) {
+        double s = x[j];
+#pragma unroll
+        for (int k = 0; k < j; ++k) s -= L[tri(j, k)] * x[k];
+        x[j] = s * L[tri(j, j)];
+    }
+}
+
+// Slow, rank-revealing fallback of the IBVS pseudo-inverse (one thread, rolled loops, local arrays):
+// x = pinv(J) b through the cyclic-Jacobi eigen-decomposition of the smaller Gram matrix, with
+// eigenvalues <= 64 eps lambda_max discarded.  J [MM x 6] row-major.  J == 0 gives x = 0, as
+// np.linalg.pinv does (experiment.py:312).
+static __device__ __noinline__ void pinv_fallback(int MM, const double* J, const double* b, double* x) {
+    const int K = MM >= 6 ? 6 : MM;
+    double A[6][6], V[6][6], rhs[6], y[6];
+    for (int i = 0; i < K; ++i)
+        for (int j = 0; j < K; ++j) {
+            double s = 0.0;
+            if (MM >= 6) for (int r = 0; r < MM; ++r) s += J[r * 6 + i] * J[r * 6 + j];
+            else for (int c = 0; c < 6; ++c) s += J[i * 6 + c] * J[j * 6 + c];
+            A[i][j] = s;
+            V[i][j] = (i == j) ? 1.0 : 0.0;
+        }
+    for (int i = 0; i < K; ++i) {
+        double s = 0.0;
+        if (MM >= 6) for (int r = 0; r < MM; ++r) s += J[r * 6 + i] * b[r];
+        else s = b[i];
+        rhs[i] = s;
+        y[i] = 0.0;
+    }
+    for (int sweep = 0; sweep < 30; ++sweep) {
+        double off = 0.0, diag = 0.0;
+        for (int i = 0; i < K; ++i) {
+            diag += A[i][i] * A[i][i];
+            for (int j = 0; j < i; ++j) off += A[i][j] * A[i][j];
+        }
+        if (!(off > 1e-40 * diag)) break;
+        for (int p = 0; p < K - 1; ++p)
+            for (int q = p + 1; q < K; ++q) {
+                const double apq = A[p][q];
+                if (apq == 0.0) continue;
+                const double theta = (A[q][q] - A[p][p]) / (2.0 * apq);
+                const double t = copysign(1.0, theta) / (fabs(theta) + sqrt(theta * theta + 1.0));
+                const double c = rsqrt(t * t + 1.0), sn = t * c;
+                for (int k = 0; k < K; ++k) {
+                    const double akp = A[k][p], akq = A[k][q];
+                    A[k][p] = c * akp - sn * akq;
+                    A[k][q] = sn * akp + c * akq;
+                }
+                for (int k = 0; k < K; ++k) {
+                    const double apk = A[p][k], aqk = A[q][k];
+                    A[p][k] = c * apk - sn * aqk;
+                    A[q][k] = sn * apk + c * aqk;
+                }
+                for (int k = 0; k < K; ++k) {
+                    const double vkp = V[k][p], vkq = V[k][q];
+                    V[k][p] = c * vkp - sn * vkq;
+                    V[k][q] = sn * vkp + c * vkq;
+                }
+            }
+    }
+    double lmax = 0.0;
+    for (int i = 0; i < K; ++i) lmax = fmax(lmax, A[i][i]);
+    const double cut = 64.0 * 2.220446049250313e-16 * lmax;
+    for (int e = 0; e < K; ++e) {
+        const double lam = A[e][e];
+        if (!(lam > cut) || !(lmax > 0.0)) continue;
+        double proj = 0.0;
+        for (int i = 0; i < K; ++i) proj += V[i][e] * rhs[i];
+        proj /= lam;
+        for (int i = 0; i < K; ++i) y[i] += V[i][e] * proj;
+    }
+    if (MM >= 6) {
+        for (int i = 0; i < 6; ++i) x[i] = y[i];
+    } else {
+        for (int c = 0; c < 6; ++c) {
+            double s = 0.0;
+            for (int r = 0; r < MM; ++r) s += J[r * 6 + c] * y[r];
+            x[c] = s;
+        }
+    }
+}
+
+// Cooperative minimum-norm least squares x = pinv(J) b  (experiment.py:312) by a group of GS lanes
+// (GS = 32: one problem per warp; GS = 8 or 2: several problems per warp, the block-diagonal family).
+// J: [M x 6] row-major in shared memory; b_lane: b_j on group lane j < M; sc: >= 56 doubles of
+// per-group shared scratch; gl = lane index inside the group.  All 32 lanes of the warp must call.
+// Fast path: Cholesky of the smaller Gram matrix (J^T J for M >= 6, J J^T for M < 6) + one step of
+// iterative refinement on the residual (corrected semi-normal equations, error ~ eps cond(J)); if a
+// Cholesky pivot is <= 1e-13 max diag (cond(J) >~ 3e6) group lane 0 runs pinv_fallback.
+// Result in x on every lane of the group.
+template <int M, int GS>
+UVS_DEV void pinv_group(const double* J, double b_lane, double* sc, int gl, double (&x)[6], int& flags) {
+    double* sG = sc;          // 21
+    double* sg = sc + 21;     // 6
+    double* sb = sc + 27;     // 8
+    double* sr = sc + 35;     // 8
+    double* sx = sc + 43;     // 6
+    constexpr int K = (M >= 6) ? 6 : M;
+    __syncwarp();
+    if (gl < M) sb[gl] = b_lane;
+    __syncwarp();
+    double L[K * (K + 1) / 2];
+    double gmax = 0.0;
+    if (M >= 6) {
+        for (int e = gl; e < 27; e += GS) {
+            if (e < 21) {
+                int i = 0;
+                while ((i + 1) * (i + 2) / 2 <= e) ++i;
+                const int j = e - i * (i + 1) / 2;
+                double s = 0.0;
+#pragma unroll
+                for (int r = 0; r < M; ++r) s += J[r * 6 + i] * J[r * 6 + j];
+                sG[e] = s;
+            } else {
+                const int i = e - 21;
+                double s = 0.0;
+#pragma unroll
+                for (int r = 0; r < M; ++r) s += J[r * 6 + i] * sb[r];
+                sg[i] = s;
+            }
+        }
+        __syncwarp();
+#pragma unroll
+        for (int i = 0; i < K * (K + 1) / 2; ++i) L[i] = sG[i];
+    } else {
+#pragma unroll
+        for (int i = 0; i < K; ++i)
+#pragma unroll
+            for (int j = 0; j <= i; ++j) {
+                double s = 0.0;
+#pragma unroll
+                for (int c = 0; c < 6; ++c) s += J[i * 6 + c] * J[j * 6 + c];
+                L[tri(i, j)] = s;
+            }
+    }
+#pragma unroll
+    for (int i = 0; i < K; ++i) gmax = fmax(gmax, L[tri(i, i)]);
+    bool ok = chol_packed<K>(L);
+#pragma unroll
+    for (int j = 0; j < K; ++j) {
+        const double inv = L[tri(j, j)];
+        ok = ok && (inv * inv * gmax * 1e-13 < 1.0);
+    }
+    // the fast path runs unconditionally (it only touches registers and this group's scratch) so
+    // that the warp-wide barriers below are reached by every lane whatever the other groups do
+    if (M >= 6) {
+        double g[K];
+#pragma unroll
+        for (int i = 0; i < K; ++i) g[i] = sg[i];
+        chol_solve<K>(L, g);
+        if (gl < M) {
+            double s = b_lane;
+#pragma unroll
+            for (int c = 0; c < 6; ++c) s -= J[gl * 6 + c] * g[c];
+            sr[gl] = s;
+        }
+        __syncwarp();
+        if (gl < 6) {
+            double s = 0.0;
+#pragma unroll
+            for (int r = 0; r < M; ++r) s += J[r * 6 + gl] * sr[r];
+            sx[gl] = s;
+        }
+        __syncwarp();
+        double d[K];
+#pragma unroll
+        for (int i = 0; i < K; ++i) d[i] = sx[i];
+        chol_solve<K>(L, d);
+#pragma unroll
+        for (int i = 0; i < 6; ++i) x[i] = g[i] + d[i];
+    } else {
+        double y[K];
+#pragma unroll
+        for (int i = 0; i < K; ++i) y[i] = sb[i];
+        chol_solve<K>(L, y);
+#pragma unroll
+        for (int c = 0; c < 6; ++c) {
+            double s = 0.0;
+#pragma unroll
+            for (int r = 0; r < M; ++r) s += J[r * 6 + c] * y[r];
+            x[c] = s;
+        }
+        double res[K];
+#pragma unroll
+        for (int r = 0; r < M; ++r) {
+            double s = sb[r];
+#pragma unroll
+            for (int c = 0; c < 6; ++c) s -= J[r * 6 + c] * x[c];
+            res[r] = s;
+        }
+        chol_solve<K>(L, res);
+#pragma unroll
+        for (int c = 0; c < 6; ++c) {
+            double s = 0.0;
+#pragma unroll
+            for (int r = 0; r < M; ++r) s += J[r * 6 + c] * res[r];
+            x[c] += s;
+        }
+    }
+    __syncwarp();
+    if (!ok) {
+        flags |= UVS_FLAG_RANK_DEFICIENT;
+        if (gl == 0) pinv_fallback(M, J, sb, sx);
+    }
+    __syncwarp();
+    if (!ok) {
+#pragma unroll
+        for (int i = 0; i < 6; ++i) x[i] = sx[i];
+    }
+    __syncwarp();
+}
+
+template <int M>
+UVS_DEV void pinv_warp(const double* J, double b_lane, double* sc, int lane, double (&x)[6], int& flags) {
+    pinv_group<M, 32>(J, b_lane, sc, lane, x, flags);
+}
+
+}  // namespace uvs

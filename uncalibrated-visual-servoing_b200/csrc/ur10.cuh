@@ -1,0 +1,124 @@
+// ur10.cuh — kinematic UR10 + pinhole camera (device side).
+// DH chain and geometric Jacobian follow /root/reference/ur10_simulation.py:97-139,204-211;
+// the camera frame is DH frame 6 and the pixel model is SURVEY.md Appendix A.
+#pragma once
+#include "common.cuh"
+
+namespace uvs {
+
+// 3x4 homogeneous transform (last row implicit 0 0 0 1), row-major
+struct Tf {
+    double r[3][3];
+    double p[3];
+};
+
+// T <- T * dh(theta, d, a, alpha)   with   dh = Rz(theta) Tz(d) Tx(a) Rx(alpha)
+// (ur10_simulation.py:204-211).  ca/sa are compile-time so that zero terms vanish.
+template <int CA, int SA>
+UVS_DEV void dh_mul(Tf& T, double theta, double d, double a) {
+    double s, c;
+    sincos(theta, &s, &c);
+    constexpr double ca = (double)CA, sa = (double)SA;
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        const double t0 = T.r[i][0], t1 = T.r[i][1], t2 = T.r[i][2];
+        const double x = c * t0 + s * t1;          // column 0 of T*A
+        const double y = c * t1 - s * t0;          // (-s t0 + c t1)
+        T.r[i][0] = x;
+        T.r[i][1] = ca * y + sa * t2;
+        T.r[i][2] = ca * t2 - sa * y;
+        T.p[i] = T.p[i] + a * x + d * t2;
+    }
+}
+
+struct UR10 {
+    Tf T[6];       // T_0_1 .. T_0_6
+};
+
+// ur10_simulation.py:97-110
+UVS_DEV void ur10_fk(const double (&q)[6], Tf& T6, UR10* all = nullptr) {
+    Tf T;
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+#pragma unroll
+        for (int j = 0; j < 3; ++j) T.r[i][j] = (i == j) ? 1.0 : 0.0;
+        T.p[i] = 0.0;
+    }
+    dh_mul<0, -1>(T, q[0], 0.128, 0.0);               if (all) all->T[0] = T;
+    dh_mul<1, 0>(T, q[1] - M_PI / 2, 0.0, 0.6127);    if (all) all->T[1] = T;
+    dh_mul<1, 0>(T, q[2], 0.0, 0.5716);               if (all) all->T[2] = T;
+    dh_mul<0, -1>(T, q[3] - M_PI / 2, 0.1639, 0.0);   if (all) all->T[3] = T;
+    dh_mul<0, 1>(T, q[4], 0.1157, 0.0);               if (all) all->T[4] = T;
+    dh_mul<1, 0>(T, q[5] + M_PI, 0.0922, 0.0);        if (all) all->T[5] = T;
+    T6 = T;
+}
+
+// ur10_simulation.py:112-139 — J[row][col], rows = (v; w), cols = joints
+UVS_DEV void ur10_jacobian(const UR10& k, double (&J)[6][6]) {
+    const double* pe = k.T[5].p;
+#pragma unroll
+    for (int i = 0; i < 6; ++i) {
+        double z[3], p[3];
+        if (i == 0) { z[0] = 0; z[1] = 0; z[2] = 1; p[0] = p[1] = p[2] = 0; }
+        else {
+            z[0] = k.T[i - 1].r[0][2]; z[1] = k.T[i - 1].r[1][2]; z[2] = k.T[i - 1].r[2][2];
+            p[0] = k.T[i - 1].p[0]; p[1] = k.T[i - 1].p[1]; p[2] = k.T[i - 1].p[2];
+        }
+        const double dx = pe[0] - p[0], dy = pe[1] - p[1], dz = pe[2] - p[2];
+        J[0][i] = z[1] * dz - z[2] * dy;
+        J[1][i] = z[2] * dx - z[0] * dz;
+        J[2][i] = z[0] * dy - z[1] * dx;
+        J[3][i] = z[0]; J[4][i] = z[1]; J[5][i] = z[2];
+    }
+}
+
+// point in the camera (DH-6) frame: pc = R^T (pw - t)
+UVS_DEV void to_camera(const Tf& T, const double* pw, double (&pc)[3]) {
+    const double dx = pw[0] - T.p[0], dy = pw[1] - T.p[1], dz = pw[2] - T.p[2];
+#pragma unroll
+    for (int j = 0; j < 3; ++j) pc[j] = T.r[0][j] * dx + T.r[1][j] * dy + T.r[2][j] * dz;
+}
+
+// pixel coordinate `axis` (0 = u, 1 = v) of world point pw; depth returned through z
+UVS_DEV double project_coord(const Tf& T, const double* pw, int axis, double& z) {
+    double pc[3];
+    to_camera(T, pw, pc);
+    z = pc[2];
+    return kPrincipal + kFocal * (axis ? pc[1] : pc[0]) / pc[2];
+}
+
+// ur10_simulation.py:188 — Euclidean camera-to-disc distance used as "Z"
+UVS_DEV double camera_distance(const Tf& T, const double* pw) {
+    const double dx = T.p[0] - pw[0], dy = T.p[1] - pw[1], dz = T.p[2] - pw[2];
+    return sqrt(dx * dx + dy * dy + dz * dz);
+}
+
+// One row of X0 = J_image kron(I2, R^T) J_geom (experiment.py:94-114).
+// coord = 2*feature + axis; u,v = raw pixel of the feature; Zc = camera_distance.
+UVS_DEV void initial_guess_row(const UR10& k, const double (&Jg)[6][6], int coord, double u, double v,
+                               double Zc, double (&row)[6]) {
+    const double f = kFocal;
+    double ji[6];
+    if ((coord & 1) == 0) {
+        ji[0] = -f / Zc; ji[1] = 0.0; ji[2] = u / Zc; ji[3] = u * v / f; ji[4] = -(f * f + u * u) / f; ji[5] = v;
+    } else {
+        ji[0] = 0.0; ji[1] = -f / Zc; ji[2] = v / Zc; ji[3] = (f * f + v * v) / f; ji[4] = -u * v / f; ji[5] = -u;
+    }
+    // w = ji * kron(I2, R^T): w[0:3] = ji[0:3] R^T, w[3:6] = ji[3:6] R^T
+    const Tf& T = k.T[5];
+    double w[6];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        w[c] = ji[0] * T.r[c][0] + ji[1] * T.r[c][1] + ji[2] * T.r[c][2];
+        w[3 + c] = ji[3] * T.r[c][0] + ji[4] * T.r[c][1] + ji[5] * T.r[c][2];
+    }
+#pragma unroll
+    for (int j = 0; j < 6; ++j) {
+        double acc = 0.0;
+#pragma unroll
+        for (int c = 0; c < 6; ++c) acc += w[c] * Jg[c][j];
+        row[j] = acc;
+    }
+}
+
+}  // namespace uvs
