@@ -29,7 +29,7 @@ namespace uvs {
 constexpr int kBlkStride = 38;
 
 template <int M>
-struct DenseConsts {          // per CTA
+struct alignas(16) DenseConsts {          // per CTA
     double R[M * M];
     double Br[M * M];         // chol(R) lower, full storage
     double Brinv[M * M];      // inverse of Br (lower)
@@ -38,7 +38,7 @@ struct DenseConsts {          // per CTA
 };
 
 template <int M, bool MCKF>
-struct DenseWS {
+struct alignas(16) DenseWS {
     static constexpr int N = 6 * M;
     static constexpr int NB = M * (M + 1) / 2;
     double P[NB * kBlkStride];

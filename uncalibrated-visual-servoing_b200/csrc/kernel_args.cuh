@@ -41,7 +41,9 @@ UVS_DEV double next_noise(HoldState& hs, const uvs_noise_params& np, double rho,
         }
     }
     const bool outl = redraw && (fabs(fresh) > 20.0);
-    const bool pair = outl || __shfl_xor_sync(UVS_FULL_MASK, outl, 1);
+    // the shuffle must be executed by every lane: no short-circuit in front of it
+    const bool partner = __shfl_xor_sync(UVS_FULL_MASK, outl, 1) != 0;
+    const bool pair = outl || partner;
     if (redraw) {
         hs.cnt_max = pair ? np.hold_cnt : 0;
         hs.cur = fresh;
