@@ -7,7 +7,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libuvs_b200.so")
+LIB_PATH = os.environ.get("UVS_B200_LIB") or os.path.join(HERE, "libuvs_b200.so")   # override: tuning builds only
 
 UVS_MAX_SWEEP = 64
 

@@ -14,6 +14,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(HERE, "build")
+# tuning builds: UVS_DENSE_MINB=<n> python build.py --out libuvs_b200_minb<n>.so ; select with UVS_B200_LIB=<path>
 LIB = os.path.join(HERE, "libuvs_b200.so")
 SOURCES = ["api.cu", "aux_kernels.cu", "blockdiag_kernels.cu", "dense_m2.cu", "dense_m6.cu", "dense_m8.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
@@ -27,11 +28,15 @@ def _deps():
            [os.path.join(os.path.dirname(HERE), "include", "uvs_b200.h"), os.path.abspath(__file__)]
 
 
-def _compile(src, verbose):
-    obj = os.path.join(OBJ, src.replace(".cu", ".o"))
-    cmd = [NVCC] + FLAGS + ["-c", os.path.join(CSRC, src), "-o", obj]
+def _extra_defs():
+    return [f"-D{k}={os.environ[k]}" for k in ("UVS_DENSE_MINB",) if os.environ.get(k)]
+
+
+def _compile(src, verbose, tag=""):
+    obj = os.path.join(OBJ, src.replace(".cu", tag + ".o"))
+    cmd = [NVCC] + FLAGS + _extra_defs() + ["-c", os.path.join(CSRC, src), "-o", obj]
     r = subprocess.run(cmd, capture_output=True, text=True)
-    log = os.path.join(OBJ, src.replace(".cu", ".ptxas.log"))
+    log = os.path.join(OBJ, src.replace(".cu", tag + ".ptxas.log"))
     with open(log, "w") as fh:
         fh.write(r.stderr)
     if r.returncode != 0:
@@ -41,20 +46,23 @@ def _compile(src, verbose):
     return obj
 
 
-def build(force=False, verbose=False):
+def build(force=False, verbose=False, out=None):
     os.makedirs(OBJ, exist_ok=True)
-    if not force and os.path.exists(LIB):
+    lib = os.path.join(HERE, out) if out else LIB
+    tag = "." + os.path.splitext(out)[0] if out else ""
+    if not force and os.path.exists(lib):
         newest = max(os.path.getmtime(p) for p in _deps())
-        if os.path.getmtime(LIB) >= newest:
-            return LIB
+        if os.path.getmtime(lib) >= newest:
+            return lib
     with cf.ThreadPoolExecutor(max_workers=min(8, len(SOURCES))) as ex:
-        objs = list(ex.map(lambda s: _compile(s, verbose), SOURCES))
-    cmd = [NVCC, "-shared", "-o", LIB] + objs + ["-gencode", "arch=compute_100a,code=sm_100a", "-cudart", "static"]
+        objs = list(ex.map(lambda s: _compile(s, verbose, tag), SOURCES))
+    cmd = [NVCC, "-shared", "-o", lib] + objs + ["-gencode", "arch=compute_100a,code=sm_100a", "-cudart", "static"]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
-    return LIB
+    return lib
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv))
+    out = sys.argv[sys.argv.index("--out") + 1] if "--out" in sys.argv else None
+    print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv, out=out))

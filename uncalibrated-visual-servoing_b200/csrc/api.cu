@@ -61,32 +61,6 @@ static int resolve_mode(const uvs_filter_params& fp, bool p_is_blocks_or_identit
     return can ? UVS_MODE_BLOCKDIAG : UVS_MODE_DENSE;
 }
 
-// launch geometry of the dense family: as many warps per CTA as shared memory allows (<= 10)
-static int dense_geometry(int m, int method, long long B, const DeviceInfo& d, int& grid, int& block) {
-    size_t per0, per1;
-    switch (m) {
-    case 2: per0 = dense_ws_bytes<2>(method, 0); per1 = dense_ws_bytes<2>(method, 1); break;
-    case 6: per0 = dense_ws_bytes<6>(method, 0); per1 = dense_ws_bytes<6>(method, 1); break;
-    case 8: per0 = dense_ws_bytes<8>(method, 0); per1 = dense_ws_bytes<8>(method, 1); break;
-    default: return set_error(UVS_ERR_INVALID, "m=%d", m);
-    }
-    const size_t per_warp = per1 - per0;
-    int warps = (int)((d.smem_optin - per0) / per_warp);
-    if (warps > 10) warps = 10;
-    if (warps < 1) return set_error(UVS_ERR_UNSUPPORTED, "workspace does not fit shared memory");
-    // two CTAs per SM when both fit (smaller m): halves the tail
-    int ctas_per_sm = 1;
-    if (2 * (per0 + warps * per_warp + 1024) <= 228 * 1024 && warps * 2 * 32 <= 2048) ctas_per_sm = 2;
-    long long need = (B + warps - 1) / warps;
-    long long g = (long long)d.sms * ctas_per_sm;
-    if (need < g) g = need;
-    if (g < 1) g = 1;
-    if (B < warps) warps = (int)B;
-    grid = (int)g;
-    block = warps * 32;
-    return 0;
-}
-
 }  // namespace uvs
 
 using namespace uvs;
@@ -130,13 +104,11 @@ static int run_replay(ReplayArgs& a, void* stream) {
     if (mode < 0) return set_error(UVS_ERR_INVALID, "UVS_MODE_BLOCKDIAG needs Q = R = NULL, a block P and no K_out");
     cudaStream_t st = (cudaStream_t)stream;
     if (mode == UVS_MODE_BLOCKDIAG) return check_cuda(launch_blockdiag_replay(m, a, d.sms, st), "blockdiag replay");
-    int grid, block;
-    if (int rc = dense_geometry(m, fp.method, a.B, d, grid, block)) return rc;
     cudaError_t e;
     switch (m) {
-    case 2: e = launch_dense_replay<2>(a, grid, block, st); break;
-    case 6: e = launch_dense_replay<6>(a, grid, block, st); break;
-    default: e = launch_dense_replay<8>(a, grid, block, st); break;
+    case 2: e = launch_dense_replay<2>(a, d.sms, st); break;
+    case 6: e = launch_dense_replay<6>(a, d.sms, st); break;
+    default: e = launch_dense_replay<8>(a, d.sms, st); break;
     }
     return check_cuda(e, "dense replay launch");
 }
@@ -239,13 +211,11 @@ int uvs_closed_loop(const uvs_closed_loop_cfg* cfg, uint64_t trial0, int64_t B,
     a.cfg = *cfg; a.io = *io; a.trial0 = trial0; a.B = B;
     cudaStream_t st = (cudaStream_t)stream;
     if (mode == UVS_MODE_BLOCKDIAG) return check_cuda(launch_blockdiag_closed_loop(m, a, d.sms, st), "blockdiag closed loop");
-    int grid, block;
-    if (int rc = dense_geometry(m, fp.method, B, d, grid, block)) return rc;
     cudaError_t e;
     switch (m) {
-    case 2: e = launch_dense_closed_loop<2>(a, grid, block, st); break;
-    case 6: e = launch_dense_closed_loop<6>(a, grid, block, st); break;
-    default: e = launch_dense_closed_loop<8>(a, grid, block, st); break;
+    case 2: e = launch_dense_closed_loop<2>(a, d.sms, st); break;
+    case 6: e = launch_dense_closed_loop<6>(a, d.sms, st); break;
+    default: e = launch_dense_closed_loop<8>(a, d.sms, st); break;
     }
     return check_cuda(e, "dense closed-loop launch");
 }

@@ -115,7 +115,7 @@ UVS_DEV double bd_step(RowState& s, const uvs_filter_params& fp, const double (&
             for (int j = 0; j < 6; ++j) {
                 double a = (1.0 / L[tri(j, j)]) * h[j];
 #pragma unroll
-                for (int i = j + 1; i < 6; ++i) a += L[tri(i, j)] * h[i];
+                for (int i = 0; i < 6; ++i) if (i > j) a += L[tri(i, j)] * h[i];
                 w[j] = a * icx[j];
             }
             double vh[6], sh = 0.0;
@@ -123,7 +123,7 @@ UVS_DEV double bd_step(RowState& s, const uvs_filter_params& fp, const double (&
             for (int i = 0; i < 6; ++i) {
                 double a = (1.0 / L[tri(i, i)]) * w[i];
 #pragma unroll
-                for (int j = 0; j < i; ++j) a += L[tri(i, j)] * w[j];
+                for (int j = 0; j < 6; ++j) if (j < i) a += L[tri(i, j)] * w[j];
                 vh[i] = a;
                 sh += h[i] * a;
             }
@@ -162,13 +162,13 @@ UVS_DEV double bd_step(RowState& s, const uvs_filter_params& fp, const double (&
 #pragma unroll
             for (int i = 0; i < 6; ++i)
 #pragma unroll
-                for (int j = 0; j <= i; ++j)
+                for (int j = 0; j < 6; ++j) if (j <= i)
                     s.P[tri(i, j)] = s.P[tri(i, j)] - K[i] * v[j] - v[i] * K[j] + sj * K[i] * K[j];
         } else {
 #pragma unroll
             for (int i = 0; i < 6; ++i)
 #pragma unroll
-                for (int j = 0; j <= i; ++j) s.P[tri(i, j)] -= K[i] * v[j];
+                for (int j = 0; j < 6; ++j) if (j <= i) s.P[tri(i, j)] -= K[i] * v[j];
         }
     }
     return kappa;
@@ -182,13 +182,13 @@ UVS_DEV void load_row_P(RowState& s, const double* P, int layout, int M, int row
 #pragma unroll
         for (int i = 0; i < 6; ++i)
 #pragma unroll
-            for (int j = 0; j <= i; ++j) s.P[tri(i, j)] = (i == j) ? 1.0 : 0.0;
+            for (int j = 0; j < 6; ++j) if (j <= i) s.P[tri(i, j)] = (i == j) ? 1.0 : 0.0;
         return;
     }
 #pragma unroll
     for (int i = 0; i < 6; ++i)
 #pragma unroll
-        for (int j = 0; j <= i; ++j)
+        for (int j = 0; j < 6; ++j) if (j <= i)
             s.P[tri(i, j)] = (layout == UVS_P_DENSE) ? P[(size_t)(6 * row + i) * N + 6 * row + j]
                                                      : P[row * 36 + i * 6 + j];
 }

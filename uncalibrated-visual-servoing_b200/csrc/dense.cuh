@@ -3,13 +3,15 @@
 // Replaces /root/reference/experiment.py:166-297 (predict, KF / MCKF / IMCC-KF / GMCKF=RMCKF
 // update, Joseph covariance update) for B independent filters.
 //
-// Data layout (per warp, in shared memory — the filter never touches HBM between frames):
-//   P    symmetric N x N stored as its M(M+1)/2 lower 6x6 blocks, each block row-major and padded
-//        to 38 doubles so that 32 lanes reading 32 different blocks with 128-bit loads hit 32
-//        different bank groups.  Diagonal blocks are kept full (both triangles identical).
-//   At   (P H^T)^T, Kt = K^T, Ut = U^T : M x N, "k-major", so a lane's 6 consecutive rows of one
-//        column are one 48-byte run (three LDS.128, broadcast across lanes sharing a block row).
-//   X    N state;  S, D  M x M.
+// Data layout (per warp; the filter never touches HBM between frames):
+//   P    symmetric N x N, kept as its M(M+1)/2 lower 6x6 blocks.  The M(M-1)/2 OFF-DIAGONAL blocks
+//        live in REGISTERS for the whole trial — lane l < NOFF owns block (bi, bj) = offdiag_of_lane(l),
+//        36 doubles — and the M diagonal blocks live in shared memory (w.Pd, full 6x6 storage, both
+//        triangles identical, stride 38 doubles).
+//   At   (P H^T)^T, Kt = K^T, Ut = U^T : M x N in shared memory, "k-major", so a lane's 6 consecutive
+//        rows of one column are one 48-byte run (three LDS.128, broadcast across lanes sharing a
+//        block row).
+//   X    N state;  S, D  M x M (shared memory).
 //
 // Algebra (H = I_M (x) h^T, A = P^- H^T, S0 = H A):
 //   KF      S = S0 + R          K = A S^-1            U = A
@@ -41,7 +43,7 @@ template <int M, bool MCKF>
 struct alignas(16) DenseWS {
     static constexpr int N = 6 * M;
     static constexpr int NB = M * (M + 1) / 2;
-    double P[NB * kBlkStride];
+    double Pd[M * kBlkStride];                  // diagonal blocks of P
     double At[M * N];
     double Kt[M * N];
     double Ut[M * N];
@@ -49,9 +51,15 @@ struct alignas(16) DenseWS {
     double S[M * M];
     double D[M * M];
     double ib[56];                              // weights / IBVS scratch (G 21, g 6, b 8, res 8, x 6)
-    double Lp[MCKF ? NB * kBlkStride : 2];      // chol(P) in the same block layout
+    double nu[M + (M & 1)];                     // innovation, read back by every lane
+    double Lp[MCKF ? NB * kBlkStride : 2];      // chol(P), all lower blocks (MCKF only)
     double Xc[MCKF ? N : 2];
     double dx[MCKF ? N : 2];                    // X - Xc, then ex, then 1/cx
+};
+
+// this lane's off-diagonal block of P (lanes >= M(M-1)/2 carry an unused zero block)
+struct PBlock {
+    double v[6][6];
 };
 
 UVS_DEV int blk_index(int bi, int bj) { return bi * (bi + 1) / 2 + bj; }
@@ -87,85 +95,96 @@ UVS_DEV void load6(const double* p, double (&v)[6]) {
     for (int i = 0; i < 3; ++i) { const double2 t = p2[i]; v[2 * i] = t.x; v[2 * i + 1] = t.y; }
 }
 
+UVS_DEV void store6(double* p, const double (&v)[6]) {
+    double2* p2 = reinterpret_cast<double2*>(p);
+#pragma unroll
+    for (int i = 0; i < 3; ++i) p2[i] = make_double2(v[2 * i], v[2 * i + 1]);
+}
+
 // ---- P0 / P in and out --------------------------------------------------------------------------
-// global P layouts: UVS_P_DENSE [N,N], UVS_P_BLOCKS [M,6,6]; src == nullptr -> identity
+// global P layouts: UVS_P_DENSE [N,N], UVS_P_BLOCKS [M,6,6]; src == nullptr -> identity.
+// The lower triangle of a dense P is what is read (the diagonal blocks are symmetrised from it).
 template <int M>
-UVS_DEV void load_P(double* Ps, const double* src, int layout, int lane) {
-    constexpr int N = 6 * M, NB = M * (M + 1) / 2;
-    for (int e = lane; e < NB * 36; e += 32) {
-        const int b = e / 36, rc = e % 36, r = rc / 6, c = rc % 6;
-        int bi = 0;
-        while ((bi + 1) * (bi + 2) / 2 <= b) ++bi;
-        const int bj = b - bi * (bi + 1) / 2;
+UVS_DEV void load_P(PBlock& pb, double* Pd, const double* src, int layout, int lane) {
+    constexpr int N = 6 * M, NOFF = M * (M - 1) / 2;
+    int bi = 1, bj = 0;
+    if (lane < NOFF) offdiag_of_lane(lane, bi, bj);
+    const bool dense = (src != nullptr) && (layout == UVS_P_DENSE) && (lane < NOFF);
+#pragma unroll
+    for (int r = 0; r < 6; ++r)
+#pragma unroll
+        for (int c = 0; c < 6; ++c) pb.v[r][c] = dense ? src[(size_t)(6 * bi + r) * N + 6 * bj + c] : 0.0;
+    for (int e = lane; e < M * 36; e += 32) {
+        const int d = e / 36, rc = e % 36, r = rc / 6, c = rc % 6;
+        const int hi = r >= c ? r : c, lo = r >= c ? c : r;
         double v;
-        if (src == nullptr) v = (bi == bj && r == c) ? 1.0 : 0.0;
-        else if (layout == UVS_P_DENSE) {
-            // symmetrise the diagonal blocks from the lower triangle
-            const int gi = 6 * bi + r, gj = 6 * bj + c;
-            v = (gi >= gj) ? src[(size_t)gi * N + gj] : src[(size_t)gj * N + gi];
-        } else {
-            v = (bi == bj) ? ((r >= c) ? src[bi * 36 + r * 6 + c] : src[bi * 36 + c * 6 + r]) : 0.0;
-        }
-        Ps[b * kBlkStride + rc] = v;
+        if (src == nullptr) v = (r == c) ? 1.0 : 0.0;
+        else if (layout == UVS_P_DENSE) v = src[(size_t)(6 * d + hi) * N + 6 * d + lo];
+        else v = src[d * 36 + hi * 6 + lo];
+        Pd[d * kBlkStride + rc] = v;
     }
 }
 
 template <int M>
-UVS_DEV void store_P(const double* Ps, double* dst, int layout, int lane) {
-    constexpr int N = 6 * M;
+UVS_DEV void store_P(const PBlock& pb, const double* Pd, double* dst, int layout, int lane) {
+    constexpr int N = 6 * M, NOFF = M * (M - 1) / 2;
     if (layout == UVS_P_DENSE) {
-        for (int e = lane; e < N * N; e += 32) {
-            const int gi = e / N, gj = e % N;
-            const int hi = gi >= gj ? gi : gj, lo = gi >= gj ? gj : gi;
-            const int bi = hi / 6, bj = lo / 6;
-            const int r = hi % 6, c = lo % 6;
-            dst[e] = Ps[blk_index(bi, bj) * kBlkStride + r * 6 + c];
+        if (lane < NOFF) {
+            int bi, bj;
+            offdiag_of_lane(lane, bi, bj);
+#pragma unroll
+            for (int r = 0; r < 6; ++r)
+#pragma unroll
+                for (int c = 0; c < 6; ++c) {
+                    dst[(size_t)(6 * bi + r) * N + 6 * bj + c] = pb.v[r][c];
+                    dst[(size_t)(6 * bj + c) * N + 6 * bi + r] = pb.v[r][c];
+                }
+        }
+        for (int e = lane; e < M * 36; e += 32) {
+            const int d = e / 36, rc = e % 36;
+            dst[(size_t)(6 * d + rc / 6) * N + 6 * d + rc % 6] = Pd[d * kBlkStride + rc];
         }
     } else {
-        for (int e = lane; e < M * 36; e += 32) {
-            const int d = e / 36;
-            dst[e] = Ps[blk_index(d, d) * kBlkStride + e % 36];
-        }
+        for (int e = lane; e < M * 36; e += 32) dst[e] = Pd[(e / 36) * kBlkStride + e % 36];
     }
 }
 
 // ---- phase 1: P <- P + Q ;  At <- (P H^T)^T ------------------------------------------------------
 template <int M>
-UVS_DEV void predict_and_A(double* Ps, double* At, const double (&h)[6], const double* Qg, int q_identity,
-                           int lane) {
+UVS_DEV void predict_and_A(PBlock& pb, double* Pd, double* At, const double (&h)[6], const double* Qg,
+                           int q_identity, int lane) {
     constexpr int N = 6 * M, NOFF = M * (M - 1) / 2;
     if (lane < NOFF) {
         int bi, bj;
         offdiag_of_lane(lane, bi, bj);
-        double* pb = Ps + blk_index(bi, bj) * kBlkStride;
-        double B[6][6];
-        load_block(pb, B);
         if (!q_identity) {
 #pragma unroll
             for (int r = 0; r < 6; ++r)
 #pragma unroll
-                for (int c = 0; c < 6; ++c) B[r][c] += __ldg(Qg + (size_t)(6 * bi + r) * N + 6 * bj + c);
-            store_block(pb, B);
+                for (int c = 0; c < 6; ++c) pb.v[r][c] += __ldg(Qg + (size_t)(6 * bi + r) * N + 6 * bj + c);
         }
         // rows 6bi.. of column bj, and (by symmetry) rows 6bj.. of column bi
+        double lo[6], hi[6];
 #pragma unroll
         for (int r = 0; r < 6; ++r) {
             double a = 0.0;
 #pragma unroll
-            for (int c = 0; c < 6; ++c) a += B[r][c] * h[c];
-            At[bj * N + 6 * bi + r] = a;
+            for (int c = 0; c < 6; ++c) a += pb.v[r][c] * h[c];
+            lo[r] = a;
         }
 #pragma unroll
         for (int c = 0; c < 6; ++c) {
             double a = 0.0;
 #pragma unroll
-            for (int r = 0; r < 6; ++r) a += B[r][c] * h[r];
-            At[bi * N + 6 * bj + c] = a;
+            for (int r = 0; r < 6; ++r) a += pb.v[r][c] * h[r];
+            hi[c] = a;
         }
+        store6(At + bj * N + 6 * bi, lo);
+        store6(At + bi * N + 6 * bj, hi);
     }
     for (int row = lane; row < N; row += 32) {
         const int d = row / 6, r = row % 6;
-        double* pr = Ps + blk_index(d, d) * kBlkStride + r * 6;
+        double* pr = Pd + d * kBlkStride + r * 6;
         double v[6];
         load6(pr, v);
         if (q_identity) {
@@ -187,14 +206,11 @@ UVS_DEV void predict_and_A(double* Ps, double* At, const double (&h)[6], const d
 // RANK2 = false: P -= Kt^T-rows x Ut^T-rows  (P[i][j] -= sum_k K[i][k] U[j][k])
 // RANK2 = true : P[i][j] -= sum_k K[i][k] V[j][k] + V[i][k] K[j][k]      (V held in Ut)
 template <int M, bool RANK2>
-UVS_DEV void rank_update(double* Ps, const double* Kt, const double* Ut, int lane) {
+UVS_DEV void rank_update(PBlock& pb, double* Pd, const double* Kt, const double* Ut, int lane) {
     constexpr int N = 6 * M, NOFF = M * (M - 1) / 2;
     if (lane < NOFF) {
         int bi, bj;
         offdiag_of_lane(lane, bi, bj);
-        double* pb = Ps + blk_index(bi, bj) * kBlkStride;
-        double B[6][6];
-        load_block(pb, B);
 #pragma unroll
         for (int k = 0; k < M; ++k) {
             double ki[6], uj[6];
@@ -203,7 +219,7 @@ UVS_DEV void rank_update(double* Ps, const double* Kt, const double* Ut, int lan
 #pragma unroll
             for (int r = 0; r < 6; ++r)
 #pragma unroll
-                for (int c = 0; c < 6; ++c) B[r][c] -= ki[r] * uj[c];
+                for (int c = 0; c < 6; ++c) pb.v[r][c] -= ki[r] * uj[c];
             if (RANK2) {
                 double vi[6], kj[6];
                 load6(Ut + k * N + 6 * bi, vi);
@@ -211,35 +227,49 @@ UVS_DEV void rank_update(double* Ps, const double* Kt, const double* Ut, int lan
 #pragma unroll
                 for (int r = 0; r < 6; ++r)
 #pragma unroll
-                    for (int c = 0; c < 6; ++c) B[r][c] -= vi[r] * kj[c];
+                    for (int c = 0; c < 6; ++c) pb.v[r][c] -= vi[r] * kj[c];
             }
         }
-        store_block(pb, B);
     }
     // diagonal blocks: 4 lanes per block, lower triangle split 6/6/6/3, mirrored on store
     {
         const int d = lane >> 2, s = lane & 3;
         if (d < M) {
             const int rowA = 5 - s, nA = 6 - s;          // rows 5,4,3,2 with 6,5,4,3 entries
-            const int rowB = s - 1;                       // rows -,0,1,- with 0,1,2,0 entries
+            const int rowB = (s == 1) ? 0 : 1;            // rows -,0,1,- with 0,1,2,0 entries
             const int nB = (s == 1) ? 1 : ((s == 2) ? 2 : 0);
-            double* pb = Ps + blk_index(d, d) * kBlkStride;
+            double* pd = Pd + d * kBlkStride;
             const double* kt = Kt + 6 * d;
             const double* ut = Ut + 6 * d;
+            double acc[6];
+            int off[6], col[6];
 #pragma unroll
             for (int e = 0; e < 6; ++e) {
                 const bool inA = e < nA;
-                const int row = inA ? rowA : rowB;
-                const int col = inA ? e : e - nA;
-                if (inA || (e - nA) < nB) {
-                    double acc = pb[row * 6 + col];
+                col[e] = inA ? e : e - nA;
+                off[e] = (inA ? rowA : rowB) * 6 + col[e];
+                if (!inA && (e - nA) >= nB) { off[e] = rowA * 6; col[e] = 0; }     // idle slot (lane s = 3)
+                acc[e] = pd[off[e]];
+            }
 #pragma unroll
-                    for (int k = 0; k < M; ++k) {
-                        acc -= kt[k * N + row] * ut[k * N + col];
-                        if (RANK2) acc -= ut[k * N + row] * kt[k * N + col];
-                    }
-                    pb[row * 6 + col] = acc;
-                    pb[col * 6 + row] = acc;
+            for (int k = 0; k < M; ++k) {
+                const double kA = kt[k * N + rowA], kB = kt[k * N + rowB];
+                double uA = 0.0, uB = 0.0;
+                if (RANK2) { uA = ut[k * N + rowA]; uB = ut[k * N + rowB]; }
+#pragma unroll
+                for (int e = 0; e < 6; ++e) {
+                    const bool inA = e < nA;
+                    acc[e] -= (inA ? kA : kB) * ut[k * N + col[e]];
+                    if (RANK2) acc[e] -= (inA ? uA : uB) * kt[k * N + col[e]];
+                }
+            }
+#pragma unroll
+            for (int e = 0; e < 6; ++e) {
+                const bool inA = e < nA;
+                if (inA || (e - nA) < nB) {
+                    const int row = inA ? rowA : rowB;
+                    pd[row * 6 + col[e]] = acc[e];
+                    pd[col[e] * 6 + row] = acc[e];
                 }
             }
         }
@@ -250,9 +280,14 @@ UVS_DEV void rank_update(double* Ps, const double* Kt, const double* Ut, int lan
 // Lp <- chol(P) in block layout; diagonal blocks hold the 6x6 factor (lower, TRUE diagonal, upper
 // part zeroed).  Returns false if P is not numerically SPD.
 template <int M>
-UVS_DEV bool block_cholesky(const double* Ps, double* Lp, int lane) {
-    constexpr int NB = M * (M + 1) / 2;
-    for (int e = lane; e < NB * kBlkStride; e += 32) Lp[e] = Ps[e];
+UVS_DEV bool block_cholesky(const PBlock& pb, const double* Pd, double* Lp, int lane) {
+    constexpr int NOFF = M * (M - 1) / 2;
+    if (lane < NOFF) {
+        int bi, bj;
+        offdiag_of_lane(lane, bi, bj);
+        store_block(Lp + blk_index(bi, bj) * kBlkStride, pb.v);
+    }
+    for (int e = lane; e < M * 36; e += 32) Lp[blk_index(e / 36, e / 36) * kBlkStride + e % 36] = Pd[(e / 36) * kBlkStride + e % 36];
     __syncwarp();
     bool ok = true;
     for (int bj = 0; bj < M; ++bj) {
@@ -263,7 +298,7 @@ UVS_DEV bool block_cholesky(const double* Ps, double* Lp, int lane) {
 #pragma unroll
             for (int i = 0; i < 6; ++i)
 #pragma unroll
-                for (int j = 0; j <= i; ++j) Ld[tri(i, j)] = pd[i * 6 + j];
+                for (int j = 0; j < 6; ++j) if (j <= i) Ld[tri(i, j)] = pd[i * 6 + j];
         }
         ok = chol_packed<6>(Ld) && ok;          // reciprocal diagonal
         __syncwarp();
@@ -274,8 +309,8 @@ UVS_DEV bool block_cholesky(const double* Ps, double* Lp, int lane) {
 #pragma unroll
             for (int a = 0; a < 6; ++a)
 #pragma unroll
-                for (int b = 0; b <= a; ++b)
-                    if (a == i && b == j) v = (a == b) ? 1.0 / Ld[tri(a, b)] : Ld[tri(a, b)];
+                for (int b = 0; b < 6; ++b)
+                    if (b <= a && a == i && b == j) v = (a == b) ? 1.0 / Ld[tri(a, b)] : Ld[tri(a, b)];
             pd[e] = v;
         }
         // (2) panel: rows of the blocks below, x <- x L_jj^-T  (forward substitution per row)
@@ -329,7 +364,7 @@ UVS_DEV void block_forward(const double* Lp, double* y, int lane) {
         for (int i = 0; i < 6; ++i) {
             double s = y[6 * bj + i];
 #pragma unroll
-            for (int k = 0; k < i; ++k) s -= pd[i * 6 + k] * yj[k];
+            for (int k = 0; k < 6; ++k) if (k < i) s -= pd[i * 6 + k] * yj[k];
             yj[i] = s / pd[i * 6 + i];
         }
         __syncwarp();
@@ -392,21 +427,27 @@ UVS_DEV void mckf_weighted_A(const double* Lp, const double* icx, const double (
 
 // ---- S = s0_scale * H Ain + Rh, factorised redundantly in every lane's registers ------------------
 // Ain: A^T-like array (M x N).  w_lane: lane i < M carries the i-th diagonal weight of W, where
-// Rh = Br W Br^T (plain_R: Rh = R).  Optionally stores S0 = H Ain (S0sm) and the matrix D used by
-// U = A + Kp D:  d_mode 1 -> D = Rh - R,  d_mode 2 -> D = dscale * R.
+// Rh = Br W Br^T (plain_R: Rh = R).  Optionally stores the matrix D used by U = A + Kp D:
+// d_mode 1 -> D = Rh - R,  d_mode 2 -> D = dscale * R.  With R = I both are diagonal and only
+// ddiag[k] = D[k][k] (shared, M doubles) is written.
 template <int M>
 UVS_DEV bool build_and_factor_S(const double* Ain, const double (&h)[6], const DenseConsts<M>& cc,
                                 double w_lane, bool plain_R, double s0_scale, double* Ssm, double* wsm,
-                                double* Dsm, int d_mode, double dscale,
+                                double* Dsm, double* ddiag, int d_mode, double dscale,
                                 double (&L)[M * (M + 1) / 2], int lane) {
     constexpr int N = 6 * M;
-    if (lane < M) wsm[lane] = w_lane;
+    if (lane < M) {
+        wsm[lane] = w_lane;
+        if (d_mode != 0 && cc.r_identity) ddiag[lane] = (d_mode == 1) ? w_lane - 1.0 : dscale;
+    }
     __syncwarp();
     for (int e = lane; e < M * M; e += 32) {
         const int i = e / M, k = e % M;
+        double a[6];
+        load6(Ain + k * N + 6 * i, a);
         double s0 = 0.0;
 #pragma unroll
-        for (int r = 0; r < 6; ++r) s0 += h[r] * Ain[k * N + 6 * i + r];
+        for (int r = 0; r < 6; ++r) s0 += h[r] * a[r];
         double rh;
         if (plain_R) rh = cc.R[e];
         else if (cc.r_identity) rh = (i == k) ? wsm[i] : 0.0;
@@ -416,14 +457,17 @@ UVS_DEV bool build_and_factor_S(const double* Ain, const double (&h)[6], const D
             for (int j = 0; j < M; ++j) rh += cc.Br[i * M + j] * wsm[j] * cc.Br[k * M + j];
         }
         Ssm[e] = s0_scale * s0 + rh;
-        if (d_mode == 1) Dsm[e] = rh - cc.R[e];
-        else if (d_mode == 2) Dsm[e] = dscale * cc.R[e];
+        if (!cc.r_identity) {
+            if (d_mode == 1) Dsm[e] = rh - cc.R[e];
+            else if (d_mode == 2) Dsm[e] = dscale * cc.R[e];
+        }
     }
     __syncwarp();
 #pragma unroll
     for (int i = 0; i < M; ++i)
 #pragma unroll
-        for (int j = 0; j <= i; ++j) L[tri(i, j)] = Ssm[i * M + j];
+        for (int j = 0; j < M; ++j)
+            if (j <= i) L[tri(i, j)] = Ssm[i * M + j];
     return chol_packed<M>(L);
 }
 
@@ -432,26 +476,32 @@ struct StepOut {
     int epoch = 0;
 };
 
-// One predict + update of the filter held in `w`.  z_lane: Z_i on lane i < M.  Returns kappa_i on
+// One predict + update of the filter held in (pb, w).  z_lane: Z_i on lane i < M.  Returns kappa_i on
 // lane i < M (experiment.py:306-308).  K^T is left in w.Kt.
 template <int M, int METHOD>
-UVS_DEV double dense_step(DenseWS<M, METHOD == UVS_METHOD_MCKF>& w, const DenseConsts<M>& cc,
+UVS_DEV double dense_step(PBlock& pb, DenseWS<M, METHOD == UVS_METHOD_MCKF>& w, const DenseConsts<M>& cc,
                           const uvs_filter_params& fp, const double (&h)[6], double z_lane, double sigma,
                           int lane, StepOut& out) {
     constexpr int N = 6 * M;
-    predict_and_A<M>(w.P, w.At, h, fp.Q, cc.q_identity, lane);
-    __syncwarp();
+    predict_and_A<M>(pb, w.Pd, w.At, h, fp.Q, cc.q_identity, lane);
 
-    // innovation nu = Z - H X, gathered on every lane
+    // innovation nu = Z - H X (lane i < M), published through shared memory
     double nu_l = 0.0;
     if (lane < M) {
+        double x[6];
+        load6(w.X + 6 * lane, x);
         nu_l = z_lane;
 #pragma unroll
-        for (int r = 0; r < 6; ++r) nu_l -= h[r] * w.X[6 * lane + r];
+        for (int r = 0; r < 6; ++r) nu_l -= h[r] * x[r];
+        w.nu[lane] = nu_l;
     }
+    __syncwarp();
     double nu[M];
 #pragma unroll
-    for (int j = 0; j < M; ++j) nu[j] = shfl_d(nu_l, j);
+    for (int j = 0; j < M; j += 2) {
+        const double2 t = *reinterpret_cast<const double2*>(w.nu + j);
+        nu[j] = t.x; nu[j + 1] = t.y;
+    }
     // whitened innovation e = Br^-1 nu
     double e_l = 0.0;
     if (lane < M) {
@@ -483,7 +533,8 @@ UVS_DEV double dense_step(DenseWS<M, METHOD == UVS_METHOD_MCKF>& w, const DenseC
             s0_scale = c; gain_scale = c; dscale = 1.0 - c;
             d_mode = fp.joseph ? 2 : 0;
         }
-        const bool ok = build_and_factor_S<M>(w.At, h, cc, w_lane, plain_R, s0_scale, w.S, w.ib, w.D, d_mode,
+        double* ddiag = w.ib + 8;
+        const bool ok = build_and_factor_S<M>(w.At, h, cc, w_lane, plain_R, s0_scale, w.S, w.ib, w.D, ddiag, d_mode,
                                               dscale, L, lane);
         if (!ok) {                       // S not SPD: skip the correction, P keeps +Q
             out.flags |= UVS_FLAG_NOT_SPD;
@@ -492,6 +543,7 @@ UVS_DEV double dense_step(DenseWS<M, METHOD == UVS_METHOD_MCKF>& w, const DenseC
             return kappa;
         }
         const bool use_D = d_mode != 0;
+        const bool diag_D = cc.r_identity != 0;
         for (int row = lane; row < N; row += 32) {
             double a[M], x[M];
 #pragma unroll
@@ -501,21 +553,26 @@ UVS_DEV double dense_step(DenseWS<M, METHOD == UVS_METHOD_MCKF>& w, const DenseC
 #pragma unroll
             for (int k = 0; k < M; ++k) {
                 w.Kt[k * N + row] = gain_scale * x[k];
-                dxr += gain_scale * x[k] * nu[k];
+                dxr += x[k] * nu[k];
             }
-            w.X[row] += dxr;                                     // experiment.py:193 / 265 / 291
+            w.X[row] += gain_scale * dxr;                        // experiment.py:193 / 265 / 291
+            if (use_D && diag_D) {
 #pragma unroll
-            for (int k = 0; k < M; ++k) {
-                double u = a[k];
-                if (use_D) {
+                for (int k = 0; k < M; ++k) w.Ut[k * N + row] = a[k] + x[k] * ddiag[k];
+            } else {
 #pragma unroll
-                    for (int j = 0; j < M; ++j) u += x[j] * w.D[j * M + k];
+                for (int k = 0; k < M; ++k) {
+                    double u = a[k];
+                    if (use_D) {
+#pragma unroll
+                        for (int j = 0; j < M; ++j) u += x[j] * w.D[j * M + k];
+                    }
+                    w.Ut[k * N + row] = u;
                 }
-                w.Ut[k * N + row] = u;
             }
         }
         __syncwarp();
-        rank_update<M, false>(w.P, w.Kt, w.Ut, lane);
+        rank_update<M, false>(pb, w.Pd, w.Kt, w.Ut, lane);
         __syncwarp();
         return kappa;
     } else {
@@ -528,7 +585,7 @@ UVS_DEV double dense_step(DenseWS<M, METHOD == UVS_METHOD_MCKF>& w, const DenseC
             for (int r = 0; r < 6; ++r) s0 += h[r] * w.At[k * N + 6 * i + r];
             w.D[e] = s0;
         }
-        const bool spd = block_cholesky<M>(w.P, w.Lp, lane);
+        const bool spd = block_cholesky<M>(pb, w.Pd, w.Lp, lane);
         for (int row = lane; row < N; row += 32) w.Xc[row] = w.X[row];
         __syncwarp();
         if (!spd) {
@@ -574,7 +631,7 @@ UVS_DEV double dense_step(DenseWS<M, METHOD == UVS_METHOD_MCKF>& w, const DenseC
             if (__any_sync(UVS_FULL_MASK, cy == 0.0)) {                 // experiment.py:231-236
                 out.flags |= UVS_FLAG_SKIP_SINGULAR; skip = true; break;
             }
-            const bool ok = build_and_factor_S<M>(Ain, h, cc, 1.0 / cy, false, 1.0, w.S, w.ib, nullptr, 0, 0.0, L, lane);
+            const bool ok = build_and_factor_S<M>(Ain, h, cc, 1.0 / cy, false, 1.0, w.S, w.ib, nullptr, nullptr, 0, 0.0, L, lane);
             if (!ok) { out.flags |= UVS_FLAG_NOT_SPD; skip = true; break; }
             // K rows, X_corrected = X + K (Z - H X)        experiment.py:238-242
             double num = 0.0, den = 0.0;
@@ -617,7 +674,7 @@ UVS_DEV double dense_step(DenseWS<M, METHOD == UVS_METHOD_MCKF>& w, const DenseC
             }
         }
         __syncwarp();
-        rank_update<M, true>(w.P, w.Kt, w.Ut, lane);
+        rank_update<M, true>(pb, w.Pd, w.Kt, w.Ut, lane);
         __syncwarp();
         return kappa;
     }

@@ -6,7 +6,16 @@
 #include "dense.cuh"
 #include "kernel_args.cuh"
 
+// CTA geometry: kDenseWarps filters per CTA, UVS_DENSE_MINB CTAs per SM asked of ptxas (register cap
+// 65536 / (MINB * 128)); the launchers size the persistent grid with the occupancy API.
+#ifndef UVS_DENSE_MINB
+#define UVS_DENSE_MINB 3
+#endif
+
 namespace uvs {
+
+constexpr int kDenseWarps = 4;
+constexpr int kDenseThreads = kDenseWarps * 32;
 
 template <int M, bool MCKF>
 __host__ __device__ constexpr size_t dense_smem_bytes(int warps) {
@@ -14,7 +23,7 @@ __host__ __device__ constexpr size_t dense_smem_bytes(int warps) {
 }
 
 template <int M, int METHOD>
-__global__ void __launch_bounds__(320) dense_replay_kernel(const __grid_constant__ ReplayArgs a) {
+__global__ void __launch_bounds__(kDenseThreads, UVS_DENSE_MINB) dense_replay_kernel(const __grid_constant__ ReplayArgs a) {
     constexpr int N = 6 * M;
     constexpr bool MCKF = METHOD == UVS_METHOD_MCKF;
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -28,7 +37,8 @@ __global__ void __launch_bounds__(320) dense_replay_kernel(const __grid_constant
 
     for (long long b = (long long)blockIdx.x * wpc + warp; b < a.B; b += (long long)gridDim.x * wpc) {
         for (int r = lane; r < N; r += 32) w.X[r] = a.X[b * N + r];
-        load_P<M>(w.P, a.P ? a.P + b * psz : nullptr, a.p_layout, lane);
+        PBlock pb;
+        load_P<M>(pb, w.Pd, a.P ? a.P + b * psz : nullptr, a.p_layout, lane);
         __syncwarp();
         double f_prev = (!a.direct && lane < M) ? a.f_init[b * M + lane] : 0.0;
         for (int k = 0; k < a.T; ++k) {
@@ -50,23 +60,23 @@ __global__ void __launch_bounds__(320) dense_replay_kernel(const __grid_constant
                 sigma = annealed_bw(a.fp.kernel_bw, a.fp.annealing, k, a.k_max);
             }
             StepOut so;
-            const double kappa = dense_step<M, METHOD>(w, cc, a.fp, h, z, sigma, lane, so);
+            const double kappa = dense_step<M, METHOD>(pb, w, cc, a.fp, h, z, sigma, lane, so);
             const size_t bt = (size_t)b * a.T + k;
             if (a.X_out) for (int r = lane; r < N; r += 32) a.X_out[bt * N + r] = w.X[r];
-            if (a.P_out) store_P<M>(w.P, a.P_out + bt * psz, a.p_layout, lane);
+            if (a.P_out) store_P<M>(pb, w.Pd, a.P_out + bt * psz, a.p_layout, lane);
             if (a.kappa_out && lane < M) a.kappa_out[bt * M + lane] = kappa;
             if (a.flags_out && lane == 0) a.flags_out[bt] = so.flags | (so.epoch << UVS_FLAG_EPOCH_SHIFT);
             if (a.K_out) for (int e = lane; e < N * M; e += 32) a.K_out[bt * N * M + e] = w.Kt[(e % M) * N + e / M];
             __syncwarp();
         }
         for (int r = lane; r < N; r += 32) a.X[b * N + r] = w.X[r];
-        if (a.P) store_P<M>(w.P, a.P + b * psz, a.p_layout, lane);
+        if (a.P) store_P<M>(pb, w.Pd, a.P + b * psz, a.p_layout, lane);
         __syncwarp();
     }
 }
 
 template <int M, int METHOD>
-__global__ void __launch_bounds__(320) dense_closed_loop_kernel(const __grid_constant__ ClosedLoopArgs a) {
+__global__ void __launch_bounds__(kDenseThreads, UVS_DENSE_MINB) dense_closed_loop_kernel(const __grid_constant__ ClosedLoopArgs a) {
     constexpr int N = 6 * M;
     constexpr bool MCKF = METHOD == UVS_METHOD_MCKF;
     constexpr int LOGW = 6 + 2 * M;
@@ -129,7 +139,8 @@ __global__ void __launch_bounds__(320) dense_closed_loop_kernel(const __grid_con
                 }
             }
         }
-        load_P<M>(w.P, cfg.P0, UVS_P_DENSE, lane);
+        PBlock pb;
+        load_P<M>(pb, w.Pd, cfg.P0, UVS_P_DENSE, lane);
         __syncwarp();
 
         HoldState hs;
@@ -162,7 +173,7 @@ __global__ void __launch_bounds__(320) dense_closed_loop_kernel(const __grid_con
             for (int r = 0; r < 6; ++r) h[r] = (k == 0) ? 0.0 : dq[r];   // experiment.py:183-188
             const double sigma = annealed_bw(cfg.filt.kernel_bw, cfg.filt.annealing, k, T);
             StepOut so;
-            const double kappa = dense_step<M, METHOD>(w, cc, cfg.filt, h, z, sigma, lane, so);
+            const double kappa = dense_step<M, METHOD>(pb, w, cc, cfg.filt, h, z, sigma, lane, so);
             flags_all |= so.flags;
 
             // IBVS: dq = -gain pinv(J) (kappa o error)                    experiment.py:300-312
@@ -208,52 +219,55 @@ __global__ void __launch_bounds__(320) dense_closed_loop_kernel(const __grid_con
         if (a.io.X_out) for (int r = lane; r < N; r += 32) a.io.X_out[b * N + r] = w.X[r];
         if (a.io.P_out) {
             const size_t psz = (a.io.p_layout == UVS_P_DENSE) ? (size_t)N * N : (size_t)M * 36;
-            store_P<M>(w.P, a.io.P_out + b * psz, a.io.p_layout, lane);
+            store_P<M>(pb, w.Pd, a.io.P_out + b * psz, a.io.p_layout, lane);
         }
         __syncwarp();
     }
 }
 
-// host-side dispatch (defined once per M in dense_m*.cu)
-template <int M> cudaError_t launch_dense_replay(const ReplayArgs& a, int grid, int block, cudaStream_t st);
-template <int M> cudaError_t launch_dense_closed_loop(const ClosedLoopArgs& a, int grid, int block, cudaStream_t st);
-template <int M> size_t dense_ws_bytes(int method, int warps);
+// host-side dispatch (defined once per M in dense_m*.cu): persistent grid = SMs x resident CTAs
+template <int M> cudaError_t launch_dense_replay(const ReplayArgs& a, int sms, cudaStream_t st);
+template <int M> cudaError_t launch_dense_closed_loop(const ClosedLoopArgs& a, int sms, cudaStream_t st);
+
+template <typename Kernel, typename Args>
+static cudaError_t dense_launch(Kernel kernel, const Args& a, long long B, size_t smem, int sms, cudaStream_t st) {
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    int per_sm = 0;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kDenseThreads, smem);
+    if (e != cudaSuccess) return e;
+    if (per_sm < 1) return cudaErrorLaunchOutOfResources;
+    long long grid = (long long)sms * per_sm;
+    const long long need = (B + kDenseWarps - 1) / kDenseWarps;
+    if (need < grid) grid = need;
+    kernel<<<(int)grid, kDenseThreads, smem, st>>>(a);
+    return cudaGetLastError();
+}
 
 #define UVS_DEFINE_DENSE_LAUNCHERS(MM)                                                                       \
-    template <> size_t dense_ws_bytes<MM>(int method, int warps) {                                           \
-        return method == UVS_METHOD_MCKF ? dense_smem_bytes<MM, true>(warps) : dense_smem_bytes<MM, false>(warps); \
+    template <int METHOD> static cudaError_t replay_one_##MM(const ReplayArgs& a, int sms, cudaStream_t st) { \
+        return dense_launch(dense_replay_kernel<MM, METHOD>, a, a.B,                                         \
+                            dense_smem_bytes<MM, METHOD == UVS_METHOD_MCKF>(kDenseWarps), sms, st);          \
     }                                                                                                        \
-    template <int METHOD> static cudaError_t replay_one_##MM(const ReplayArgs& a, int grid, int block, cudaStream_t st) { \
-        const size_t smem = dense_ws_bytes<MM>(METHOD, block / 32);                                          \
-        cudaError_t e = cudaFuncSetAttribute(dense_replay_kernel<MM, METHOD>,                                \
-                                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);        \
-        if (e != cudaSuccess) return e;                                                                      \
-        dense_replay_kernel<MM, METHOD><<<grid, block, smem, st>>>(a);                                       \
-        return cudaGetLastError();                                                                           \
+    template <int METHOD> static cudaError_t closed_one_##MM(const ClosedLoopArgs& a, int sms, cudaStream_t st) { \
+        return dense_launch(dense_closed_loop_kernel<MM, METHOD>, a, a.B,                                    \
+                            dense_smem_bytes<MM, METHOD == UVS_METHOD_MCKF>(kDenseWarps), sms, st);          \
     }                                                                                                        \
-    template <int METHOD> static cudaError_t closed_one_##MM(const ClosedLoopArgs& a, int grid, int block, cudaStream_t st) { \
-        const size_t smem = dense_ws_bytes<MM>(METHOD, block / 32);                                          \
-        cudaError_t e = cudaFuncSetAttribute(dense_closed_loop_kernel<MM, METHOD>,                           \
-                                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);        \
-        if (e != cudaSuccess) return e;                                                                      \
-        dense_closed_loop_kernel<MM, METHOD><<<grid, block, smem, st>>>(a);                                  \
-        return cudaGetLastError();                                                                           \
-    }                                                                                                        \
-    template <> cudaError_t launch_dense_replay<MM>(const ReplayArgs& a, int grid, int block, cudaStream_t st) { \
+    template <> cudaError_t launch_dense_replay<MM>(const ReplayArgs& a, int sms, cudaStream_t st) {         \
         switch (a.fp.method) {                                                                               \
-        case UVS_METHOD_KF: return replay_one_##MM<UVS_METHOD_KF>(a, grid, block, st);                       \
-        case UVS_METHOD_MCKF: return replay_one_##MM<UVS_METHOD_MCKF>(a, grid, block, st);                   \
-        case UVS_METHOD_IMCCKF: return replay_one_##MM<UVS_METHOD_IMCCKF>(a, grid, block, st);               \
-        case UVS_METHOD_GMCKF: return replay_one_##MM<UVS_METHOD_GMCKF>(a, grid, block, st);                 \
+        case UVS_METHOD_KF: return replay_one_##MM<UVS_METHOD_KF>(a, sms, st);                               \
+        case UVS_METHOD_MCKF: return replay_one_##MM<UVS_METHOD_MCKF>(a, sms, st);                           \
+        case UVS_METHOD_IMCCKF: return replay_one_##MM<UVS_METHOD_IMCCKF>(a, sms, st);                       \
+        case UVS_METHOD_GMCKF: return replay_one_##MM<UVS_METHOD_GMCKF>(a, sms, st);                         \
         default: return cudaErrorInvalidValue;                                                               \
         }                                                                                                    \
     }                                                                                                        \
-    template <> cudaError_t launch_dense_closed_loop<MM>(const ClosedLoopArgs& a, int grid, int block, cudaStream_t st) { \
+    template <> cudaError_t launch_dense_closed_loop<MM>(const ClosedLoopArgs& a, int sms, cudaStream_t st) { \
         switch (a.cfg.filt.method) {                                                                         \
-        case UVS_METHOD_KF: return closed_one_##MM<UVS_METHOD_KF>(a, grid, block, st);                       \
-        case UVS_METHOD_MCKF: return closed_one_##MM<UVS_METHOD_MCKF>(a, grid, block, st);                   \
-        case UVS_METHOD_IMCCKF: return closed_one_##MM<UVS_METHOD_IMCCKF>(a, grid, block, st);               \
-        case UVS_METHOD_GMCKF: return closed_one_##MM<UVS_METHOD_GMCKF>(a, grid, block, st);                 \
+        case UVS_METHOD_KF: return closed_one_##MM<UVS_METHOD_KF>(a, sms, st);                               \
+        case UVS_METHOD_MCKF: return closed_one_##MM<UVS_METHOD_MCKF>(a, sms, st);                           \
+        case UVS_METHOD_IMCCKF: return closed_one_##MM<UVS_METHOD_IMCCKF>(a, sms, st);                       \
+        case UVS_METHOD_GMCKF: return closed_one_##MM<UVS_METHOD_GMCKF>(a, sms, st);                         \
         default: return cudaErrorInvalidValue;                                                               \
         }                                                                                                    \
     }
