@@ -342,7 +342,7 @@ __global__ void __launch_bounds__(128) bd_closed_loop_kernel(const __grid_consta
             if (!__any_sync(UVS_FULL_MASK, alive)) break;
             const double t = (double)(k + 1) * cfg.dt;
             Tf T6;
-            ur10_fk(q, T6);
+            ur10_fk_group<GS>(q, gl, T6);
             double depth;
             const double f_true = project_coord(T6, cfg.targets + 3 * (row >> 1), row & 1, depth);
             if (cfg.fov_check) {

@@ -149,10 +149,13 @@ __global__ void __launch_bounds__(kDenseThreads, UVS_DENSE_MINB) dense_closed_lo
         int status = UVS_STATUS_SUCCESS, frames = 0, flags_all = 0;
         const double desired = (lane < M) ? cfg.desired_f[lane] : 0.0;
 
+        constexpr int FB = 32 / M;         // frames of noise drawn at once: lane = slot * M + coordinate
+        const bool philox = (a.io.noise_in == nullptr) && (cfg.noise.type != UVS_NOISE_NONE);
+        double fresh_batch = 0.0;
         for (int k = 0; k < T; ++k) {
             const double t = (double)(k + 1) * cfg.dt;
             Tf T6;
-            ur10_fk(q, T6);
+            ur10_fk_group<32>(q, lane, T6);
             double f_true = 0.0, depth = 1.0;
             if (lane < M) f_true = project_coord(T6, cfg.targets + 3 * (lane >> 1), lane & 1, depth);
             if (cfg.fov_check) {
@@ -161,10 +164,18 @@ __global__ void __launch_bounds__(kDenseThreads, UVS_DENSE_MINB) dense_closed_lo
                     status = UVS_STATUS_FAIL; flags_all |= UVS_FLAG_OUT_OF_VIEW; break;
                 }
             }
-            double nz;
+            double nz = 0.0;
             if (a.io.noise_in) nz = (lane < M) ? a.io.noise_in[((size_t)b * T + k) * M + lane] : 0.0;
-            else if (cfg.noise.type == UVS_NOISE_NONE) nz = 0.0;
-            else nz = next_noise(hs, cfg.noise, rho, alpha, trial, (uint32_t)k, lane, M);
+            else if (philox) {
+                const int slot = k % FB;
+                if (slot == 0) {
+                    const int fs = lane / M;
+                    if (fs < FB && k + fs < T)
+                        fresh_batch = noise_sample(cfg.noise, rho, alpha, trial, (uint32_t)(k + fs), (uint32_t)(lane % M));
+                }
+                const double fresh = shfl_d(fresh_batch, slot * M + (lane % M));
+                nz = next_noise_prefetched(hs, cfg.noise.hold_cnt, fresh, lane, M);
+            }
             const double f_new = f_true + nz;                            // experiment.py:130-135
             const double z = f_new - f_l;                                // experiment.py:170-177
             f_l = f_new;

@@ -51,6 +51,24 @@ UVS_DEV double next_noise(HoldState& hs, const uvs_noise_params& np, double rho,
     return hs.cur;
 }
 
+// Same hold logic when this frame's fresh draw was computed ahead of time (counter-based streams make
+// the draw a pure function of (trial, frame, coordinate), so it can be evaluated by an otherwise idle
+// lane several frames early).  Every lane of the warp must call.
+UVS_DEV double next_noise_prefetched(HoldState& hs, int hold_cnt, double fresh, int lane, int M) {
+    bool redraw = false;
+    if (lane < M) {
+        if (hs.cnt >= hs.cnt_max) { hs.cnt = 0; redraw = true; }
+        else hs.cnt += 1;
+    }
+    const bool outl = redraw && (fabs(fresh) > 20.0);
+    const bool partner = __shfl_xor_sync(UVS_FULL_MASK, outl, 1) != 0;
+    if (redraw) {
+        hs.cnt_max = (outl || partner) ? hold_cnt : 0;
+        hs.cur = fresh;
+    }
+    return hs.cur;
+}
+
 UVS_DEV void start_pose(const uvs_closed_loop_cfg& cfg, uint64_t trial, double (&q)[6]) {
 #pragma unroll
     for (int j = 0; j < 6; ++j) q[j] = cfg.q_start[j];

@@ -13,11 +13,10 @@ struct Tf {
 };
 
 // T <- T * dh(theta, d, a, alpha)   with   dh = Rz(theta) Tz(d) Tx(a) Rx(alpha)
-// (ur10_simulation.py:204-211).  ca/sa are compile-time so that zero terms vanish.
+// (ur10_simulation.py:204-211), given s = sin(theta), c = cos(theta).  ca/sa are compile-time so that
+// zero terms vanish.
 template <int CA, int SA>
-UVS_DEV void dh_mul(Tf& T, double theta, double d, double a) {
-    double s, c;
-    sincos(theta, &s, &c);
+UVS_DEV void dh_mul(Tf& T, double s, double c, double d, double a) {
     constexpr double ca = (double)CA, sa = (double)SA;
 #pragma unroll
     for (int i = 0; i < 3; ++i) {
@@ -35,8 +34,13 @@ struct UR10 {
     Tf T[6];       // T_0_1 .. T_0_6
 };
 
-// ur10_simulation.py:97-110
-UVS_DEV void ur10_fk(const double (&q)[6], Tf& T6, UR10* all = nullptr) {
+// joint angle -> DH theta (ur10_simulation.py:100-105)
+UVS_DEV double dh_theta(int j, double qj) {
+    return (j == 1 || j == 3) ? qj - M_PI / 2 : ((j == 5) ? qj + M_PI : qj);
+}
+
+// the DH chain given sin/cos of the six thetas
+UVS_DEV void ur10_chain(const double (&s)[6], const double (&c)[6], Tf& T6, UR10* all = nullptr) {
     Tf T;
 #pragma unroll
     for (int i = 0; i < 3; ++i) {
@@ -44,13 +48,45 @@ UVS_DEV void ur10_fk(const double (&q)[6], Tf& T6, UR10* all = nullptr) {
         for (int j = 0; j < 3; ++j) T.r[i][j] = (i == j) ? 1.0 : 0.0;
         T.p[i] = 0.0;
     }
-    dh_mul<0, -1>(T, q[0], 0.128, 0.0);               if (all) all->T[0] = T;
-    dh_mul<1, 0>(T, q[1] - M_PI / 2, 0.0, 0.6127);    if (all) all->T[1] = T;
-    dh_mul<1, 0>(T, q[2], 0.0, 0.5716);               if (all) all->T[2] = T;
-    dh_mul<0, -1>(T, q[3] - M_PI / 2, 0.1639, 0.0);   if (all) all->T[3] = T;
-    dh_mul<0, 1>(T, q[4], 0.1157, 0.0);               if (all) all->T[4] = T;
-    dh_mul<1, 0>(T, q[5] + M_PI, 0.0922, 0.0);        if (all) all->T[5] = T;
+    dh_mul<0, -1>(T, s[0], c[0], 0.128, 0.0);    if (all) all->T[0] = T;
+    dh_mul<1, 0>(T, s[1], c[1], 0.0, 0.6127);    if (all) all->T[1] = T;
+    dh_mul<1, 0>(T, s[2], c[2], 0.0, 0.5716);    if (all) all->T[2] = T;
+    dh_mul<0, -1>(T, s[3], c[3], 0.1639, 0.0);   if (all) all->T[3] = T;
+    dh_mul<0, 1>(T, s[4], c[4], 0.1157, 0.0);    if (all) all->T[4] = T;
+    dh_mul<1, 0>(T, s[5], c[5], 0.0922, 0.0);    if (all) all->T[5] = T;
     T6 = T;
+}
+
+// ur10_simulation.py:97-110 — every thread evaluates all six sincos
+UVS_DEV void ur10_fk(const double (&q)[6], Tf& T6, UR10* all = nullptr) {
+    double s[6], c[6];
+#pragma unroll
+    for (int j = 0; j < 6; ++j) sincos(dh_theta(j, q[j]), &s[j], &c[j]);
+    ur10_chain(s, c, T6, all);
+}
+
+// Same result, for a group of GS lanes that all hold the same q: the six sincos evaluations (the
+// expensive part) are split over the lanes of the group and exchanged with shuffles; gl = lane index
+// in the group.  Every lane of the warp must call.
+template <int GS>
+UVS_DEV void ur10_fk_group(const double (&q)[6], int gl, Tf& T6) {
+    constexpr int SLOTS = (6 + GS - 1) / GS;
+    double ss[SLOTS], cs[SLOTS];
+#pragma unroll
+    for (int t = 0; t < SLOTS; ++t) {
+        double th = 0.0;
+#pragma unroll
+        for (int j = 0; j < 6; ++j)
+            if (j / GS == t && j % GS == gl) th = dh_theta(j, q[j]);
+        sincos(th, &ss[t], &cs[t]);
+    }
+    double s[6], c[6];
+#pragma unroll
+    for (int j = 0; j < 6; ++j) {
+        s[j] = __shfl_sync(UVS_FULL_MASK, ss[j / GS], j % GS, GS);
+        c[j] = __shfl_sync(UVS_FULL_MASK, cs[j / GS], j % GS, GS);
+    }
+    ur10_chain(s, c, T6);
 }
 
 // ur10_simulation.py:112-139 — J[row][col], rows = (v; w), cols = joints
