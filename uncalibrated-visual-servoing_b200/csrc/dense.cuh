@@ -26,6 +26,11 @@
 #include "common.cuh"
 #include "smallmat.cuh"
 
+// 1: the gain phase reads chol(S) from shared memory (frees 2 x M(M+1)/2 registers); 0: from registers
+#ifndef UVS_DENSE_L_SMEM
+#define UVS_DENSE_L_SMEM 1
+#endif
+
 namespace uvs {
 
 constexpr int kBlkStride = 38;
@@ -52,6 +57,10 @@ struct alignas(16) DenseWS {
     double D[M * M];
     double ib[56];                              // weights / IBVS scratch (G 21, g 6, b 8, res 8, x 6)
     double nu[M + (M & 1)];                     // innovation, read back by every lane
+    double Lc[M * (M + 1) / 2 + ((M * (M + 1) / 2) & 1)];   // chol(S), packed lower, reciprocal diagonal
+    double q[6];                                // closed loop: joint positions, the last command,
+    double dq[6];                               // and sin/cos of the DH angles of this frame
+    double sc[12];
     double Lp[MCKF ? NB * kBlkStride : 2];      // chol(P), all lower blocks (MCKF only)
     double Xc[MCKF ? N : 2];
     double dx[MCKF ? N : 2];                    // X - Xc, then ex, then 1/cx
@@ -60,6 +69,7 @@ struct alignas(16) DenseWS {
 // this lane's off-diagonal block of P (lanes >= M(M-1)/2 carry an unused zero block)
 struct PBlock {
     double v[6][6];
+    int bi, bj;          // block row / column (bi > bj); lanes without a block carry (1, 0) and never use it
 };
 
 UVS_DEV int blk_index(int bi, int bj) { return bi * (bi + 1) / 2 + bj; }
@@ -109,6 +119,7 @@ UVS_DEV void load_P(PBlock& pb, double* Pd, const double* src, int layout, int l
     constexpr int N = 6 * M, NOFF = M * (M - 1) / 2;
     int bi = 1, bj = 0;
     if (lane < NOFF) offdiag_of_lane(lane, bi, bj);
+    pb.bi = bi; pb.bj = bj;
     const bool dense = (src != nullptr) && (layout == UVS_P_DENSE) && (lane < NOFF);
 #pragma unroll
     for (int r = 0; r < 6; ++r)
@@ -130,8 +141,7 @@ UVS_DEV void store_P(const PBlock& pb, const double* Pd, double* dst, int layout
     constexpr int N = 6 * M, NOFF = M * (M - 1) / 2;
     if (layout == UVS_P_DENSE) {
         if (lane < NOFF) {
-            int bi, bj;
-            offdiag_of_lane(lane, bi, bj);
+            const int bi = pb.bi, bj = pb.bj;
 #pragma unroll
             for (int r = 0; r < 6; ++r)
 #pragma unroll
@@ -155,8 +165,7 @@ UVS_DEV void predict_and_A(PBlock& pb, double* Pd, double* At, const double (&h)
                            int q_identity, int lane) {
     constexpr int N = 6 * M, NOFF = M * (M - 1) / 2;
     if (lane < NOFF) {
-        int bi, bj;
-        offdiag_of_lane(lane, bi, bj);
+        const int bi = pb.bi, bj = pb.bj;
         if (!q_identity) {
 #pragma unroll
             for (int r = 0; r < 6; ++r)
@@ -209,8 +218,7 @@ template <int M, bool RANK2>
 UVS_DEV void rank_update(PBlock& pb, double* Pd, const double* Kt, const double* Ut, int lane) {
     constexpr int N = 6 * M, NOFF = M * (M - 1) / 2;
     if (lane < NOFF) {
-        int bi, bj;
-        offdiag_of_lane(lane, bi, bj);
+        const int bi = pb.bi, bj = pb.bj;
 #pragma unroll
         for (int k = 0; k < M; ++k) {
             double ki[6], uj[6];
@@ -231,46 +239,46 @@ UVS_DEV void rank_update(PBlock& pb, double* Pd, const double* Kt, const double*
             }
         }
     }
-    // diagonal blocks: 4 lanes per block, lower triangle split 6/6/6/3, mirrored on store
+    // diagonal blocks: 4 lanes per block.  Lane s owns row rowA = 5 - s (columns 0..rowA) and, for s = 1, 2,
+    // row rowB = s - 1 (columns 0..rowB): 6 + 6 + 6 + 3 = 21 lower entries.  All four lanes load the block
+    // row's six U values (broadcast) and their own two K values, and run 6 + 2 FMAs per k on fixed
+    // registers; entries outside the lane's set are computed and dropped.
     {
         const int d = lane >> 2, s = lane & 3;
         if (d < M) {
-            const int rowA = 5 - s, nA = 6 - s;          // rows 5,4,3,2 with 6,5,4,3 entries
-            const int rowB = (s == 1) ? 0 : 1;            // rows -,0,1,- with 0,1,2,0 entries
-            const int nB = (s == 1) ? 1 : ((s == 2) ? 2 : 0);
+            const int rowA = 5 - s;
+            const int rowB = (s == 2) ? 1 : 0;
             double* pd = Pd + d * kBlkStride;
             const double* kt = Kt + 6 * d;
             const double* ut = Ut + 6 * d;
-            double acc[6];
-            int off[6], col[6];
-#pragma unroll
-            for (int e = 0; e < 6; ++e) {
-                const bool inA = e < nA;
-                col[e] = inA ? e : e - nA;
-                off[e] = (inA ? rowA : rowB) * 6 + col[e];
-                if (!inA && (e - nA) >= nB) { off[e] = rowA * 6; col[e] = 0; }     // idle slot (lane s = 3)
-                acc[e] = pd[off[e]];
-            }
+            double accA[6], accB[2];
+            load6(pd + rowA * 6, accA);
+            accB[0] = pd[rowB * 6]; accB[1] = pd[rowB * 6 + 1];
 #pragma unroll
             for (int k = 0; k < M; ++k) {
+                double u[6];
+                load6(ut + k * N, u);
                 const double kA = kt[k * N + rowA], kB = kt[k * N + rowB];
-                double uA = 0.0, uB = 0.0;
-                if (RANK2) { uA = ut[k * N + rowA]; uB = ut[k * N + rowB]; }
 #pragma unroll
-                for (int e = 0; e < 6; ++e) {
-                    const bool inA = e < nA;
-                    acc[e] -= (inA ? kA : kB) * ut[k * N + col[e]];
-                    if (RANK2) acc[e] -= (inA ? uA : uB) * kt[k * N + col[e]];
+                for (int e = 0; e < 6; ++e) accA[e] -= kA * u[e];
+                accB[0] -= kB * u[0];
+                accB[1] -= kB * u[1];
+                if (RANK2) {
+                    double kk[6];
+                    load6(kt + k * N, kk);
+                    const double uA = ut[k * N + rowA], uB = ut[k * N + rowB];
+#pragma unroll
+                    for (int e = 0; e < 6; ++e) accA[e] -= uA * kk[e];
+                    accB[0] -= uB * kk[0];
+                    accB[1] -= uB * kk[1];
                 }
             }
 #pragma unroll
-            for (int e = 0; e < 6; ++e) {
-                const bool inA = e < nA;
-                if (inA || (e - nA) < nB) {
-                    const int row = inA ? rowA : rowB;
-                    pd[row * 6 + col[e]] = acc[e];
-                    pd[col[e] * 6 + row] = acc[e];
-                }
+            for (int e = 0; e < 6; ++e)
+                if (e <= rowA) { pd[rowA * 6 + e] = accA[e]; pd[e * 6 + rowA] = accA[e]; }
+            if (s == 1 || s == 2) {
+                pd[rowB * 6] = accB[0]; pd[rowB] = accB[0];
+                if (s == 2) { pd[rowB * 6 + 1] = accB[1]; pd[6 + rowB] = accB[1]; }
             }
         }
     }
@@ -283,9 +291,7 @@ template <int M>
 UVS_DEV bool block_cholesky(const PBlock& pb, const double* Pd, double* Lp, int lane) {
     constexpr int NOFF = M * (M - 1) / 2;
     if (lane < NOFF) {
-        int bi, bj;
-        offdiag_of_lane(lane, bi, bj);
-        store_block(Lp + blk_index(bi, bj) * kBlkStride, pb.v);
+        store_block(Lp + blk_index(pb.bi, pb.bj) * kBlkStride, pb.v);
     }
     for (int e = lane; e < M * 36; e += 32) Lp[blk_index(e / 36, e / 36) * kBlkStride + e % 36] = Pd[(e / 36) * kBlkStride + e % 36];
     __syncwarp();
@@ -471,6 +477,26 @@ UVS_DEV bool build_and_factor_S(const double* Ain, const double (&h)[6], const D
     return chol_packed<M>(L);
 }
 
+// x <- (L L^T)^-1 x with L (packed lower, reciprocal diagonal) read from shared memory: every access is
+// a warp-wide broadcast with a compile-time offset, so L costs no registers in the gain phase.
+template <int M>
+UVS_DEV void chol_solve_sm(const double* Ls, double (&x)[M]) {
+#pragma unroll
+    for (int j = 0; j < M; ++j) {
+        double s = x[j];
+#pragma unroll
+        for (int k = 0; k < M; ++k) if (k < j) s -= Ls[tri(j, k)] * x[k];
+        x[j] = s * Ls[tri(j, j)];
+    }
+#pragma unroll
+    for (int j = M - 1; j >= 0; --j) {
+        double s = x[j];
+#pragma unroll
+        for (int k = 0; k < M; ++k) if (k > j) s -= Ls[tri(k, j)] * x[k];
+        x[j] = s * Ls[tri(j, j)];
+    }
+}
+
 struct StepOut {
     int flags = 0;
     int epoch = 0;
@@ -496,19 +522,13 @@ UVS_DEV double dense_step(PBlock& pb, DenseWS<M, METHOD == UVS_METHOD_MCKF>& w, 
         w.nu[lane] = nu_l;
     }
     __syncwarp();
-    double nu[M];
-#pragma unroll
-    for (int j = 0; j < M; j += 2) {
-        const double2 t = *reinterpret_cast<const double2*>(w.nu + j);
-        nu[j] = t.x; nu[j + 1] = t.y;
-    }
     // whitened innovation e = Br^-1 nu
     double e_l = 0.0;
     if (lane < M) {
         if (cc.r_identity) e_l = nu_l;
         else {
 #pragma unroll
-            for (int j = 0; j < M; ++j) e_l += cc.Brinv[lane * M + j] * nu[j];
+            for (int j = 0; j < M; ++j) e_l += cc.Brinv[lane * M + j] * w.nu[j];
         }
     }
     double kappa = 1.0;
@@ -544,11 +564,34 @@ UVS_DEV double dense_step(PBlock& pb, DenseWS<M, METHOD == UVS_METHOD_MCKF>& w, 
         }
         const bool use_D = d_mode != 0;
         const bool diag_D = cc.r_identity != 0;
+#if UVS_DENSE_L_SMEM
+        {   // every lane holds the same factor: publish it once, then let the registers go
+            constexpr int NL = M * (M + 1) / 2;
+#pragma unroll
+            for (int i = 0; i + 1 < NL; i += 2) *reinterpret_cast<double2*>(w.Lc + i) = make_double2(L[i], L[i + 1]);
+            if (NL & 1) w.Lc[NL - 1] = L[NL - 1];
+            __syncwarp();
+        }
+#endif
+        double nu[M];
+#pragma unroll
+        for (int j = 0; j < M; j += 2) {
+            const double2 t = *reinterpret_cast<const double2*>(w.nu + j);
+            nu[j] = t.x; nu[j + 1] = t.y;
+        }
         for (int row = lane; row < N; row += 32) {
             double a[M], x[M];
 #pragma unroll
             for (int k = 0; k < M; ++k) { a[k] = w.At[k * N + row]; x[k] = a[k]; }
+#if UVS_DENSE_L_SMEM
+            {
+                const double* Ls = w.Lc;
+                asm volatile("" : "+l"(Ls));                      // keep the loads inside the loop (no hoisting into registers)
+                chol_solve_sm<M>(Ls, x);
+            }
+#else
             chol_solve<M>(L, x);                                  // Kp row = A row S^-1
+#endif
             double dxr = 0.0;
 #pragma unroll
             for (int k = 0; k < M; ++k) {
@@ -577,6 +620,12 @@ UVS_DEV double dense_step(PBlock& pb, DenseWS<M, METHOD == UVS_METHOD_MCKF>& w, 
         return kappa;
     } else {
         // ------------------------------------------------------------------ MCKF (experiment.py:194-250)
+        double nu[M];
+#pragma unroll
+        for (int j = 0; j < M; j += 2) {
+            const double2 t = *reinterpret_cast<const double2*>(w.nu + j);
+            nu[j] = t.x; nu[j + 1] = t.y;
+        }
         // S0 of the TRUE predicted covariance is needed by the Joseph form
         for (int e = lane; e < M * M; e += 32) {
             const int i = e / M, k = e % M;

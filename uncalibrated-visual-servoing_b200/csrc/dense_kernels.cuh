@@ -9,12 +9,15 @@
 // CTA geometry: kDenseWarps filters per CTA, UVS_DENSE_MINB CTAs per SM asked of ptxas (register cap
 // 65536 / (MINB * 128)); the launchers size the persistent grid with the occupancy API.
 #ifndef UVS_DENSE_MINB
-#define UVS_DENSE_MINB 3
+#define UVS_DENSE_MINB 2
 #endif
 
 namespace uvs {
 
-constexpr int kDenseWarps = 4;
+#ifndef UVS_DENSE_WARPS
+#define UVS_DENSE_WARPS 4
+#endif
+constexpr int kDenseWarps = UVS_DENSE_WARPS;
 constexpr int kDenseThreads = kDenseWarps * 32;
 
 template <int M, bool MCKF>
@@ -99,15 +102,18 @@ __global__ void __launch_bounds__(kDenseThreads, UVS_DENSE_MINB) dense_closed_lo
             if (lvl >= cfg.sweep_len) lvl = cfg.sweep_len - 1;
             if (cfg.sweep_param == 1) rho = cfg.sweep[lvl]; else alpha = cfg.sweep[lvl];
         }
-        double q[6];
-        if (a.io.q0_in) {
-#pragma unroll
-            for (int j = 0; j < 6; ++j) q[j] = a.io.q0_in[b * 6 + j];
-        } else start_pose(cfg, trial, q);
-
-        // ---- initial state (experiment.py:70-117) ---------------------------------------------
         double f_l = 0.0;              // this lane's feature coordinate (noisy, as logged)
         {
+            double q[6];
+            if (a.io.q0_in) {
+#pragma unroll
+                for (int j = 0; j < 6; ++j) q[j] = a.io.q0_in[b * 6 + j];
+            } else start_pose(cfg, trial, q);
+#pragma unroll
+            for (int j = 0; j < 6; ++j)
+                if (lane == j) { w.q[j] = q[j]; w.dq[j] = 0.0; }
+
+            // ---- initial state (experiment.py:70-117) -----------------------------------------
             UR10 kin;
             Tf T6;
             ur10_fk(q, T6, &kin);
@@ -145,19 +151,37 @@ __global__ void __launch_bounds__(kDenseThreads, UVS_DENSE_MINB) dense_closed_lo
 
         HoldState hs;
         double ise = 0.0, iae = 0.0, itae = 0.0;
-        double dq[6] = {0, 0, 0, 0, 0, 0};
         int status = UVS_STATUS_SUCCESS, frames = 0, flags_all = 0;
         const double desired = (lane < M) ? cfg.desired_f[lane] : 0.0;
+        const double* target = cfg.targets + 3 * ((lane < M ? lane : 0) >> 1);
 
         constexpr int FB = 32 / M;         // frames of noise drawn at once: lane = slot * M + coordinate
         const bool philox = (a.io.noise_in == nullptr) && (cfg.noise.type != UVS_NOISE_NONE);
         double fresh_batch = 0.0;
         for (int k = 0; k < T; ++k) {
-            const double t = (double)(k + 1) * cfg.dt;
-            Tf T6;
-            ur10_fk_group<32>(q, lane, T6);
+            // ---- plant: joint angles -> this lane's feature coordinate ------------------------------
+            // lane j < 6 evaluates sin/cos of DH angle j; lanes < M walk their target point back through
+            // the chain into the camera frame (ur10_simulation.py:97-110 + SURVEY Appendix A pixel model)
+            double q_l = 0.0;
+            if (lane < 6) {
+                q_l = w.q[lane];
+                double sn, cs;
+                sincos(dh_theta(lane, q_l), &sn, &cs);
+                *reinterpret_cast<double2*>(w.sc + 2 * lane) = make_double2(sn, cs);
+            }
+            __syncwarp();
             double f_true = 0.0, depth = 1.0;
-            if (lane < M) f_true = project_coord(T6, cfg.targets + 3 * (lane >> 1), lane & 1, depth);
+            if (lane < M) {
+                double sn[6], cs[6], pc[3];
+#pragma unroll
+                for (int j = 0; j < 6; ++j) {
+                    const double2 t = *reinterpret_cast<const double2*>(w.sc + 2 * j);
+                    sn[j] = t.x; cs[j] = t.y;
+                }
+                ur10_point_in_camera(sn, cs, target, pc);
+                f_true = pixel_of(pc, lane & 1);
+                depth = pc[2];
+            }
             if (cfg.fov_check) {
                 const bool bad = (lane < M) && !(f_true >= 0.0 && f_true < kResolution && depth > kMinDepth);
                 if (__any_sync(UVS_FULL_MASK, bad)) {                   // NaN centroid -> FAIL
@@ -179,23 +203,26 @@ __global__ void __launch_bounds__(kDenseThreads, UVS_DENSE_MINB) dense_closed_lo
             const double f_new = f_true + nz;                            // experiment.py:130-135
             const double z = f_new - f_l;                                // experiment.py:170-177
             f_l = f_new;
-            double h[6];
-#pragma unroll
-            for (int r = 0; r < 6; ++r) h[r] = (k == 0) ? 0.0 : dq[r];   // experiment.py:183-188
             const double sigma = annealed_bw(cfg.filt.kernel_bw, cfg.filt.annealing, k, T);
             StepOut so;
-            const double kappa = dense_step<M, METHOD>(pb, w, cc, cfg.filt, h, z, sigma, lane, so);
+            double kappa;
+            {
+                double h[6];                                             // experiment.py:183-188: the previous
+                load6(w.dq, h);                                          // command (zeros on the first frame)
+                kappa = dense_step<M, METHOD>(pb, w, cc, cfg.filt, h, z, sigma, lane, so);
+            }
             flags_all |= so.flags;
 
             // IBVS: dq = -gain pinv(J) (kappa o error)                    experiment.py:300-312
-            const double err = f_l - desired;
             double x[6];
             int ib_flags = 0;
-            pinv_warp<M>(w.X, kappa * err, w.ib, lane, x, ib_flags);
+            pinv_warp<M>(w.X, kappa * (f_l - desired), w.ib, lane, x, ib_flags);
             flags_all |= ib_flags;
-            bool bad = false;
+            double dq_l = 0.0;
 #pragma unroll
-            for (int r = 0; r < 6; ++r) { dq[r] = -cfg.ibvs_gain * x[r]; bad = bad || !isfinite(dq[r]); }
+            for (int r = 0; r < 6; ++r)
+                if (lane == r) dq_l = -cfg.ibvs_gain * x[r];
+            bool bad = !isfinite(dq_l);
             for (int r = lane; r < N; r += 32) bad = bad || !isfinite(w.X[r]);
             if (__any_sync(UVS_FULL_MASK, bad)) {                        // experiment.py:313-316
                 status = UVS_STATUS_FAIL; flags_all |= UVS_FLAG_NONFINITE; break;
@@ -203,17 +230,20 @@ __global__ void __launch_bounds__(kDenseThreads, UVS_DENSE_MINB) dense_closed_lo
             // logging (experiment.py:323-331) and error integrals (plot_errorbar.m:39-84)
             if (a.io.log) {
                 double* lg = a.io.log + ((size_t)b * T + k) * LOGW;
-#pragma unroll
-                for (int r = 0; r < 6; ++r) if (lane == r) lg[r] = q[r];
+                if (lane < 6) lg[lane] = q_l;
                 if (lane < M) { lg[6 + lane] = f_l; lg[6 + M + lane] = nz; }
             }
             if (lane < M) {
+                const double t = (double)(k + 1) * cfg.dt;
                 const double e = desired - f_l;
                 ise += e * e; iae += fabs(e); itae += t * fabs(e);
             }
             ++frames;
-#pragma unroll
-            for (int r = 0; r < 6; ++r) q[r] += dq[r] * cfg.dt;          // experiment.py:320,335
+            if (lane < 6) {                                              // experiment.py:320,335
+                w.dq[lane] = dq_l;
+                w.q[lane] = q_l + dq_l * cfg.dt;
+            }
+            __syncwarp();
         }
         // ||.||_2 over the M coordinates
         double s0 = ise * ise, s1 = iae * iae, s2 = itae * itae;

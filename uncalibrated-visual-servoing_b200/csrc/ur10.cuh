@@ -57,19 +57,36 @@ UVS_DEV void ur10_chain(const double (&s)[6], const double (&c)[6], Tf& T6, UR10
     T6 = T;
 }
 
-// ur10_simulation.py:97-110 — every thread evaluates all six sincos
-UVS_DEV void ur10_fk(const double (&q)[6], Tf& T6, UR10* all = nullptr) {
-    double s[6], c[6];
-#pragma unroll
-    for (int j = 0; j < 6; ++j) sincos(dh_theta(j, q[j]), &s[j], &c[j]);
-    ur10_chain(s, c, T6, all);
+// p <- dh(theta, d, a, alpha)^-1 p : the point seen from the next link frame.  With A = [R | t],
+// R = Rz(theta) Rx(alpha), t = (a c, a s, d):  A^-1 p = R^T (p - t) = Rx(-alpha) (Rz(-theta) p - (a, 0, d)).
+template <int CA, int SA>
+UVS_DEV void dh_inv_point(double (&p)[3], double s, double c, double d, double a) {
+    constexpr double ca = (double)CA, sa = (double)SA;
+    const double xr = c * p[0] + s * p[1] - a;
+    const double yr = c * p[1] - s * p[0];
+    const double zr = p[2] - d;
+    p[0] = xr;
+    p[1] = ca * yr + sa * zr;
+    p[2] = ca * zr - sa * yr;
 }
 
-// Same result, for a group of GS lanes that all hold the same q: the six sincos evaluations (the
-// expensive part) are split over the lanes of the group and exchanged with shuffles; gl = lane index
-// in the group.  Every lane of the warp must call.
+// World point -> camera (DH frame 6) coordinates by walking the chain backwards: 6 x ~6 flops instead of
+// the ~110 of the forward matrix chain + R^T (p - t).  Same value up to rounding (a few ulp).
+UVS_DEV void ur10_point_in_camera(const double (&s)[6], const double (&c)[6], const double* pw, double (&pc)[3]) {
+    pc[0] = pw[0]; pc[1] = pw[1]; pc[2] = pw[2];
+    dh_inv_point<0, -1>(pc, s[0], c[0], 0.128, 0.0);
+    dh_inv_point<1, 0>(pc, s[1], c[1], 0.0, 0.6127);
+    dh_inv_point<1, 0>(pc, s[2], c[2], 0.0, 0.5716);
+    dh_inv_point<0, -1>(pc, s[3], c[3], 0.1639, 0.0);
+    dh_inv_point<0, 1>(pc, s[4], c[4], 0.1157, 0.0);
+    dh_inv_point<1, 0>(pc, s[5], c[5], 0.0922, 0.0);
+}
+
+// sin / cos of the six DH thetas for a group of GS lanes that all hold the same q: the evaluations are
+// split over the lanes of the group and exchanged with shuffles; gl = lane index in the group.  Every
+// lane of the warp must call.
 template <int GS>
-UVS_DEV void ur10_fk_group(const double (&q)[6], int gl, Tf& T6) {
+UVS_DEV void ur10_sincos_group(const double (&q)[6], int gl, double (&s)[6], double (&c)[6]) {
     constexpr int SLOTS = (6 + GS - 1) / GS;
     double ss[SLOTS], cs[SLOTS];
 #pragma unroll
@@ -80,12 +97,31 @@ UVS_DEV void ur10_fk_group(const double (&q)[6], int gl, Tf& T6) {
             if (j / GS == t && j % GS == gl) th = dh_theta(j, q[j]);
         sincos(th, &ss[t], &cs[t]);
     }
-    double s[6], c[6];
 #pragma unroll
     for (int j = 0; j < 6; ++j) {
         s[j] = __shfl_sync(UVS_FULL_MASK, ss[j / GS], j % GS, GS);
         c[j] = __shfl_sync(UVS_FULL_MASK, cs[j / GS], j % GS, GS);
     }
+}
+
+// pixel coordinate `axis` of a camera-frame point (SURVEY Appendix A pixel model)
+UVS_DEV double pixel_of(const double (&pc)[3], int axis) {
+    return kPrincipal + kFocal * (axis ? pc[1] : pc[0]) / pc[2];
+}
+
+// ur10_simulation.py:97-110 — every thread evaluates all six sincos
+UVS_DEV void ur10_fk(const double (&q)[6], Tf& T6, UR10* all = nullptr) {
+    double s[6], c[6];
+#pragma unroll
+    for (int j = 0; j < 6; ++j) sincos(dh_theta(j, q[j]), &s[j], &c[j]);
+    ur10_chain(s, c, T6, all);
+}
+
+// Same result for a group of GS lanes that all hold the same q (sincos split over the lanes).
+template <int GS>
+UVS_DEV void ur10_fk_group(const double (&q)[6], int gl, Tf& T6) {
+    double s[6], c[6];
+    ur10_sincos_group<GS>(q, gl, s, c);
     ur10_chain(s, c, T6);
 }
 
