@@ -47,11 +47,12 @@ struct alignas(16) DenseConsts {          // per CTA
 template <int M, bool MCKF>
 struct alignas(16) DenseWS {
     static constexpr int N = 6 * M;
+    static constexpr int LD = N + 2;           // row stride of At/Kt/Ut: 8(N+2) B is an odd number of 16-B bank groups
     static constexpr int NB = M * (M + 1) / 2;
     double Pd[M * kBlkStride];                  // diagonal blocks of P
-    double At[M * N];
-    double Kt[M * N];
-    double Ut[M * N];
+    double At[M * LD];
+    double Kt[M * LD];
+    double Ut[M * LD];
     double X[N];
     double S[M * M];
     double D[M * M];
@@ -116,7 +117,7 @@ UVS_DEV void store6(double* p, const double (&v)[6]) {
 // The lower triangle of a dense P is what is read (the diagonal blocks are symmetrised from it).
 template <int M>
 UVS_DEV void load_P(PBlock& pb, double* Pd, const double* src, int layout, int lane) {
-    constexpr int N = 6 * M, NOFF = M * (M - 1) / 2;
+    constexpr int N = 6 * M, LD = N + 2, NOFF = M * (M - 1) / 2;
     int bi = 1, bj = 0;
     if (lane < NOFF) offdiag_of_lane(lane, bi, bj);
     pb.bi = bi; pb.bj = bj;
@@ -138,7 +139,7 @@ UVS_DEV void load_P(PBlock& pb, double* Pd, const double* src, int layout, int l
 
 template <int M>
 UVS_DEV void store_P(const PBlock& pb, const double* Pd, double* dst, int layout, int lane) {
-    constexpr int N = 6 * M, NOFF = M * (M - 1) / 2;
+    constexpr int N = 6 * M, LD = N + 2, NOFF = M * (M - 1) / 2;
     if (layout == UVS_P_DENSE) {
         if (lane < NOFF) {
             const int bi = pb.bi, bj = pb.bj;
@@ -163,7 +164,7 @@ UVS_DEV void store_P(const PBlock& pb, const double* Pd, double* dst, int layout
 template <int M>
 UVS_DEV void predict_and_A(PBlock& pb, double* Pd, double* At, const double (&h)[6], const double* Qg,
                            int q_identity, int lane) {
-    constexpr int N = 6 * M, NOFF = M * (M - 1) / 2;
+    constexpr int N = 6 * M, LD = N + 2, NOFF = M * (M - 1) / 2;
     if (lane < NOFF) {
         const int bi = pb.bi, bj = pb.bj;
         if (!q_identity) {
@@ -188,8 +189,8 @@ UVS_DEV void predict_and_A(PBlock& pb, double* Pd, double* At, const double (&h)
             for (int r = 0; r < 6; ++r) a += pb.v[r][c] * h[r];
             hi[c] = a;
         }
-        store6(At + bj * N + 6 * bi, lo);
-        store6(At + bi * N + 6 * bj, hi);
+        store6(At + bj * LD + 6 * bi, lo);
+        store6(At + bi * LD + 6 * bj, hi);
     }
     for (int row = lane; row < N; row += 32) {
         const int d = row / 6, r = row % 6;
@@ -207,7 +208,7 @@ UVS_DEV void predict_and_A(PBlock& pb, double* Pd, double* At, const double (&h)
         double a = 0.0;
 #pragma unroll
         for (int c = 0; c < 6; ++c) a += v[c] * h[c];
-        At[d * N + row] = a;
+        At[d * LD + row] = a;
     }
 }
 
@@ -216,22 +217,22 @@ UVS_DEV void predict_and_A(PBlock& pb, double* Pd, double* At, const double (&h)
 // RANK2 = true : P[i][j] -= sum_k K[i][k] V[j][k] + V[i][k] K[j][k]      (V held in Ut)
 template <int M, bool RANK2>
 UVS_DEV void rank_update(PBlock& pb, double* Pd, const double* Kt, const double* Ut, int lane) {
-    constexpr int N = 6 * M, NOFF = M * (M - 1) / 2;
+    constexpr int N = 6 * M, LD = N + 2, NOFF = M * (M - 1) / 2;
     if (lane < NOFF) {
         const int bi = pb.bi, bj = pb.bj;
 #pragma unroll
         for (int k = 0; k < M; ++k) {
             double ki[6], uj[6];
-            load6(Kt + k * N + 6 * bi, ki);
-            load6(Ut + k * N + 6 * bj, uj);
+            load6(Kt + k * LD + 6 * bi, ki);
+            load6(Ut + k * LD + 6 * bj, uj);
 #pragma unroll
             for (int r = 0; r < 6; ++r)
 #pragma unroll
                 for (int c = 0; c < 6; ++c) pb.v[r][c] -= ki[r] * uj[c];
             if (RANK2) {
                 double vi[6], kj[6];
-                load6(Ut + k * N + 6 * bi, vi);
-                load6(Kt + k * N + 6 * bj, kj);
+                load6(Ut + k * LD + 6 * bi, vi);
+                load6(Kt + k * LD + 6 * bj, kj);
 #pragma unroll
                 for (int r = 0; r < 6; ++r)
 #pragma unroll
@@ -257,16 +258,16 @@ UVS_DEV void rank_update(PBlock& pb, double* Pd, const double* Kt, const double*
 #pragma unroll
             for (int k = 0; k < M; ++k) {
                 double u[6];
-                load6(ut + k * N, u);
-                const double kA = kt[k * N + rowA], kB = kt[k * N + rowB];
+                load6(ut + k * LD, u);
+                const double kA = kt[k * LD + rowA], kB = kt[k * LD + rowB];
 #pragma unroll
                 for (int e = 0; e < 6; ++e) accA[e] -= kA * u[e];
                 accB[0] -= kB * u[0];
                 accB[1] -= kB * u[1];
                 if (RANK2) {
                     double kk[6];
-                    load6(kt + k * N, kk);
-                    const double uA = ut[k * N + rowA], uB = ut[k * N + rowB];
+                    load6(kt + k * LD, kk);
+                    const double uA = ut[k * LD + rowA], uB = ut[k * LD + rowB];
 #pragma unroll
                     for (int e = 0; e < 6; ++e) accA[e] -= uA * kk[e];
                     accB[0] -= uB * kk[0];
@@ -362,7 +363,7 @@ UVS_DEV bool block_cholesky(const PBlock& pb, const double* Pd, double* Lp, int 
 // y <- Bp^-1 y  (block forward substitution, y in shared memory, length N)
 template <int M>
 UVS_DEV void block_forward(const double* Lp, double* y, int lane) {
-    constexpr int N = 6 * M;
+    constexpr int N = 6 * M, LD = N + 2;
     for (int bj = 0; bj < M; ++bj) {
         const double* pd = Lp + blk_index(bj, bj) * kBlkStride;
         double yj[6];
@@ -392,8 +393,8 @@ UVS_DEV void block_forward(const double* Lp, double* y, int lane) {
 template <int M>
 UVS_DEV void mckf_weighted_A(const double* Lp, const double* icx, const double (&h)[6], double* T1t,
                              double* Ahat_t, int lane) {
-    constexpr int N = 6 * M, NB = M * (M + 1) / 2;
-    for (int e = lane; e < M * N; e += 32) T1t[e] = 0.0;
+    constexpr int N = 6 * M, LD = N + 2, NB = M * (M + 1) / 2;
+    for (int e = lane; e < M * LD; e += 32) T1t[e] = 0.0;
     __syncwarp();
     // T1[6bj+c][k] = icx * sum_r Lp[6k+r][6bj+c] h_r   over blocks (k, bj), bj <= k
     for (int b = lane; b < NB; b += 32) {
@@ -407,7 +408,7 @@ UVS_DEV void mckf_weighted_A(const double* Lp, const double* icx, const double (
             double s = 0.0;
 #pragma unroll
             for (int r = 0; r < 6; ++r) s += B[r][c] * h[r];
-            T1t[k * N + 6 * bj + c] = s * icx[6 * bj + c];
+            T1t[k * LD + 6 * bj + c] = s * icx[6 * bj + c];
         }
     }
     __syncwarp();
@@ -419,14 +420,14 @@ UVS_DEV void mckf_weighted_A(const double* Lp, const double* icx, const double (
         for (int bj = 0; bj <= lim; ++bj) {
             double B[6][6], t[6];
             load_block(Lp + blk_index(bi, bj) * kBlkStride, B);
-            load6(T1t + k * N + 6 * bj, t);
+            load6(T1t + k * LD + 6 * bj, t);
 #pragma unroll
             for (int r = 0; r < 6; ++r)
 #pragma unroll
                 for (int c = 0; c < 6; ++c) acc[r] += B[r][c] * t[c];
         }
 #pragma unroll
-        for (int r = 0; r < 6; ++r) Ahat_t[k * N + 6 * bi + r] = acc[r];
+        for (int r = 0; r < 6; ++r) Ahat_t[k * LD + 6 * bi + r] = acc[r];
     }
     __syncwarp();
 }
@@ -441,7 +442,7 @@ UVS_DEV bool build_and_factor_S(const double* Ain, const double (&h)[6], const D
                                 double w_lane, bool plain_R, double s0_scale, double* Ssm, double* wsm,
                                 double* Dsm, double* ddiag, int d_mode, double dscale,
                                 double (&L)[M * (M + 1) / 2], int lane) {
-    constexpr int N = 6 * M;
+    constexpr int N = 6 * M, LD = N + 2;
     if (lane < M) {
         wsm[lane] = w_lane;
         if (d_mode != 0 && cc.r_identity) ddiag[lane] = (d_mode == 1) ? w_lane - 1.0 : dscale;
@@ -450,7 +451,7 @@ UVS_DEV bool build_and_factor_S(const double* Ain, const double (&h)[6], const D
     for (int e = lane; e < M * M; e += 32) {
         const int i = e / M, k = e % M;
         double a[6];
-        load6(Ain + k * N + 6 * i, a);
+        load6(Ain + k * LD + 6 * i, a);
         double s0 = 0.0;
 #pragma unroll
         for (int r = 0; r < 6; ++r) s0 += h[r] * a[r];
@@ -477,23 +478,42 @@ UVS_DEV bool build_and_factor_S(const double* Ain, const double (&h)[6], const D
     return chol_packed<M>(L);
 }
 
-// x <- (L L^T)^-1 x with L (packed lower, reciprocal diagonal) read from shared memory: every access is
-// a warp-wide broadcast with a compile-time offset, so L costs no registers in the gain phase.
-template <int M>
-UVS_DEV void chol_solve_sm(const double* Ls, double (&x)[M]) {
+// x_r <- (L L^T)^-1 x_r for R right-hand sides at once, with L (packed lower, reciprocal diagonal) read from
+// shared memory: every access is a warp-wide broadcast with a compile-time offset, so L costs no registers in
+// the gain phase, and the R substitutions are independent dependency chains the scheduler can interleave.
+template <int M, int R>
+UVS_DEV void chol_solve_sm(const double* Ls, double (&x)[R][M]) {
 #pragma unroll
     for (int j = 0; j < M; ++j) {
-        double s = x[j];
+        double s[R];
 #pragma unroll
-        for (int k = 0; k < M; ++k) if (k < j) s -= Ls[tri(j, k)] * x[k];
-        x[j] = s * Ls[tri(j, j)];
+        for (int r = 0; r < R; ++r) s[r] = x[r][j];
+#pragma unroll
+        for (int k = 0; k < M; ++k)
+            if (k < j) {
+                const double l = Ls[tri(j, k)];
+#pragma unroll
+                for (int r = 0; r < R; ++r) s[r] -= l * x[r][k];
+            }
+        const double d = Ls[tri(j, j)];
+#pragma unroll
+        for (int r = 0; r < R; ++r) x[r][j] = s[r] * d;
     }
 #pragma unroll
     for (int j = M - 1; j >= 0; --j) {
-        double s = x[j];
+        double s[R];
 #pragma unroll
-        for (int k = 0; k < M; ++k) if (k > j) s -= Ls[tri(k, j)] * x[k];
-        x[j] = s * Ls[tri(j, j)];
+        for (int r = 0; r < R; ++r) s[r] = x[r][j];
+#pragma unroll
+        for (int k = 0; k < M; ++k)
+            if (k > j) {
+                const double l = Ls[tri(k, j)];
+#pragma unroll
+                for (int r = 0; r < R; ++r) s[r] -= l * x[r][k];
+            }
+        const double d = Ls[tri(j, j)];
+#pragma unroll
+        for (int r = 0; r < R; ++r) x[r][j] = s[r] * d;
     }
 }
 
@@ -508,7 +528,7 @@ template <int M, int METHOD>
 UVS_DEV double dense_step(PBlock& pb, DenseWS<M, METHOD == UVS_METHOD_MCKF>& w, const DenseConsts<M>& cc,
                           const uvs_filter_params& fp, const double (&h)[6], double z_lane, double sigma,
                           int lane, StepOut& out) {
-    constexpr int N = 6 * M;
+    constexpr int N = 6 * M, LD = N + 2;
     predict_and_A<M>(pb, w.Pd, w.At, h, fp.Q, cc.q_identity, lane);
 
     // innovation nu = Z - H X (lane i < M), published through shared memory
@@ -558,7 +578,7 @@ UVS_DEV double dense_step(PBlock& pb, DenseWS<M, METHOD == UVS_METHOD_MCKF>& w, 
                                               dscale, L, lane);
         if (!ok) {                       // S not SPD: skip the correction, P keeps +Q
             out.flags |= UVS_FLAG_NOT_SPD;
-            for (int e = lane; e < M * N; e += 32) w.Kt[e] = 0.0;
+            for (int e = lane; e < M * LD; e += 32) w.Kt[e] = 0.0;
             __syncwarp();
             return kappa;
         }
@@ -567,9 +587,11 @@ UVS_DEV double dense_step(PBlock& pb, DenseWS<M, METHOD == UVS_METHOD_MCKF>& w, 
 #if UVS_DENSE_L_SMEM
         {   // every lane holds the same factor: publish it once, then let the registers go
             constexpr int NL = M * (M + 1) / 2;
+            if (lane == 0) {                                  // one writer: a same-address STS.128 from 32 lanes costs 4 wavefronts
 #pragma unroll
-            for (int i = 0; i + 1 < NL; i += 2) *reinterpret_cast<double2*>(w.Lc + i) = make_double2(L[i], L[i + 1]);
-            if (NL & 1) w.Lc[NL - 1] = L[NL - 1];
+                for (int i = 0; i + 1 < NL; i += 2) *reinterpret_cast<double2*>(w.Lc + i) = make_double2(L[i], L[i + 1]);
+                if (NL & 1) w.Lc[NL - 1] = L[NL - 1];
+            }
             __syncwarp();
         }
 #endif
@@ -579,38 +601,48 @@ UVS_DEV double dense_step(PBlock& pb, DenseWS<M, METHOD == UVS_METHOD_MCKF>& w, 
             const double2 t = *reinterpret_cast<const double2*>(w.nu + j);
             nu[j] = t.x; nu[j + 1] = t.y;
         }
-        for (int row = lane; row < N; row += 32) {
-            double a[M], x[M];
+        // Gain rows.  N > 32: lanes 0..N/2-1 take rows (lane, lane + N/2) and run the two triangular solves as
+        // one interleaved instruction stream (two independent dependency chains, each factor entry read once).
+        constexpr int RPL = (N > 32) ? 2 : 1, NROWL = N / RPL;
+        if (lane < NROWL) {
+            double a[RPL][M], x[RPL][M];
 #pragma unroll
-            for (int k = 0; k < M; ++k) { a[k] = w.At[k * N + row]; x[k] = a[k]; }
+            for (int j = 0; j < RPL; ++j)
+#pragma unroll
+                for (int k = 0; k < M; ++k) { a[j][k] = w.At[k * LD + lane + j * NROWL]; x[j][k] = a[j][k]; }
 #if UVS_DENSE_L_SMEM
             {
                 const double* Ls = w.Lc;
-                asm volatile("" : "+l"(Ls));                      // keep the loads inside the loop (no hoisting into registers)
-                chol_solve_sm<M>(Ls, x);
+                asm volatile("" : "+l"(Ls));                      // keep the loads inside the block (no hoisting into registers)
+                chol_solve_sm<M, RPL>(Ls, x);
             }
 #else
-            chol_solve<M>(L, x);                                  // Kp row = A row S^-1
+#pragma unroll
+            for (int j = 0; j < RPL; ++j) chol_solve<M>(L, x[j]);  // Kp row = A row S^-1
 #endif
-            double dxr = 0.0;
 #pragma unroll
-            for (int k = 0; k < M; ++k) {
-                w.Kt[k * N + row] = gain_scale * x[k];
-                dxr += x[k] * nu[k];
-            }
-            w.X[row] += gain_scale * dxr;                        // experiment.py:193 / 265 / 291
-            if (use_D && diag_D) {
-#pragma unroll
-                for (int k = 0; k < M; ++k) w.Ut[k * N + row] = a[k] + x[k] * ddiag[k];
-            } else {
+            for (int j = 0; j < RPL; ++j) {
+                const int row = lane + j * NROWL;
+                double dxr = 0.0;
 #pragma unroll
                 for (int k = 0; k < M; ++k) {
-                    double u = a[k];
-                    if (use_D) {
+                    w.Kt[k * LD + row] = gain_scale * x[j][k];
+                    dxr += x[j][k] * nu[k];
+                }
+                w.X[row] += gain_scale * dxr;                    // experiment.py:193 / 265 / 291
+                if (use_D && diag_D) {
 #pragma unroll
-                        for (int j = 0; j < M; ++j) u += x[j] * w.D[j * M + k];
+                    for (int k = 0; k < M; ++k) w.Ut[k * LD + row] = a[j][k] + x[j][k] * ddiag[k];
+                } else {
+#pragma unroll
+                    for (int k = 0; k < M; ++k) {
+                        double u = a[j][k];
+                        if (use_D) {
+#pragma unroll
+                            for (int jj = 0; jj < M; ++jj) u += x[j][jj] * w.D[jj * M + k];
+                        }
+                        w.Ut[k * LD + row] = u;
                     }
-                    w.Ut[k * N + row] = u;
                 }
             }
         }
@@ -631,7 +663,7 @@ UVS_DEV double dense_step(PBlock& pb, DenseWS<M, METHOD == UVS_METHOD_MCKF>& w, 
             const int i = e / M, k = e % M;
             double s0 = 0.0;
 #pragma unroll
-            for (int r = 0; r < 6; ++r) s0 += h[r] * w.At[k * N + 6 * i + r];
+            for (int r = 0; r < 6; ++r) s0 += h[r] * w.At[k * LD + 6 * i + r];
             w.D[e] = s0;
         }
         const bool spd = block_cholesky<M>(pb, w.Pd, w.Lp, lane);
@@ -687,11 +719,11 @@ UVS_DEV double dense_step(PBlock& pb, DenseWS<M, METHOD == UVS_METHOD_MCKF>& w, 
             for (int row = lane; row < N; row += 32) {
                 double x[M];
 #pragma unroll
-                for (int k = 0; k < M; ++k) x[k] = Ain[k * N + row];
+                for (int k = 0; k < M; ++k) x[k] = Ain[k * LD + row];
                 chol_solve<M>(L, x);
                 double xc = w.X[row];
 #pragma unroll
-                for (int k = 0; k < M; ++k) { w.Kt[k * N + row] = x[k]; xc += x[k] * nu[k]; }
+                for (int k = 0; k < M; ++k) { w.Kt[k * LD + row] = x[k]; xc += x[k] * nu[k]; }
                 const double old = w.Xc[row];
                 num += (xc - old) * (xc - old);
                 den += old * old;
@@ -713,13 +745,13 @@ UVS_DEV double dense_step(PBlock& pb, DenseWS<M, METHOD == UVS_METHOD_MCKF>& w, 
             w.X[row] = w.Xc[row];
             double kr[M];
 #pragma unroll
-            for (int k = 0; k < M; ++k) kr[k] = w.Kt[k * N + row];
+            for (int k = 0; k < M; ++k) kr[k] = w.Kt[k * LD + row];
 #pragma unroll
             for (int k = 0; k < M; ++k) {
-                double v = w.At[k * N + row];
+                double v = w.At[k * LD + row];
 #pragma unroll
                 for (int j = 0; j < M; ++j) v -= 0.5 * kr[j] * (w.D[j * M + k] + cc.R[j * M + k]);
-                w.Ut[k * N + row] = v;
+                w.Ut[k * LD + row] = v;
             }
         }
         __syncwarp();

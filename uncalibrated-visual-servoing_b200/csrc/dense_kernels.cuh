@@ -5,11 +5,18 @@
 #pragma once
 #include "dense.cuh"
 #include "kernel_args.cuh"
+#include <cstdlib>
 
 // CTA geometry: kDenseWarps filters per CTA, UVS_DENSE_MINB CTAs per SM asked of ptxas (register cap
 // 65536 / (MINB * 128)); the launchers size the persistent grid with the occupancy API.
 #ifndef UVS_DENSE_MINB
 #define UVS_DENSE_MINB 2
+#endif
+
+#ifdef UVS_DENSE_MAXNREG
+#define UVS_DENSE_BOUNDS __maxnreg__(UVS_DENSE_MAXNREG)
+#else
+#define UVS_DENSE_BOUNDS __launch_bounds__(kDenseThreads, UVS_DENSE_MINB)
 #endif
 
 namespace uvs {
@@ -26,7 +33,7 @@ __host__ __device__ constexpr size_t dense_smem_bytes(int warps) {
 }
 
 template <int M, int METHOD>
-__global__ void __launch_bounds__(kDenseThreads, UVS_DENSE_MINB) dense_replay_kernel(const __grid_constant__ ReplayArgs a) {
+__global__ void UVS_DENSE_BOUNDS dense_replay_kernel(const __grid_constant__ ReplayArgs a) {
     constexpr int N = 6 * M;
     constexpr bool MCKF = METHOD == UVS_METHOD_MCKF;
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -69,7 +76,7 @@ __global__ void __launch_bounds__(kDenseThreads, UVS_DENSE_MINB) dense_replay_ke
             if (a.P_out) store_P<M>(pb, w.Pd, a.P_out + bt * psz, a.p_layout, lane);
             if (a.kappa_out && lane < M) a.kappa_out[bt * M + lane] = kappa;
             if (a.flags_out && lane == 0) a.flags_out[bt] = so.flags | (so.epoch << UVS_FLAG_EPOCH_SHIFT);
-            if (a.K_out) for (int e = lane; e < N * M; e += 32) a.K_out[bt * N * M + e] = w.Kt[(e % M) * N + e / M];
+            if (a.K_out) for (int e = lane; e < N * M; e += 32) a.K_out[bt * N * M + e] = w.Kt[(e % M) * (N + 2) + e / M];
             __syncwarp();
         }
         for (int r = lane; r < N; r += 32) a.X[b * N + r] = w.X[r];
@@ -79,7 +86,7 @@ __global__ void __launch_bounds__(kDenseThreads, UVS_DENSE_MINB) dense_replay_ke
 }
 
 template <int M, int METHOD>
-__global__ void __launch_bounds__(kDenseThreads, UVS_DENSE_MINB) dense_closed_loop_kernel(const __grid_constant__ ClosedLoopArgs a) {
+__global__ void UVS_DENSE_BOUNDS dense_closed_loop_kernel(const __grid_constant__ ClosedLoopArgs a) {
     constexpr int N = 6 * M;
     constexpr bool MCKF = METHOD == UVS_METHOD_MCKF;
     constexpr int LOGW = 6 + 2 * M;
@@ -278,6 +285,10 @@ static cudaError_t dense_launch(Kernel kernel, const Args& a, long long B, size_
     e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kDenseThreads, smem);
     if (e != cudaSuccess) return e;
     if (per_sm < 1) return cudaErrorLaunchOutOfResources;
+    if (const char* lim = getenv("UVS_DENSE_CTAS_PER_SM")) {      // tuning experiments only
+        const int v = atoi(lim);
+        if (v >= 1 && v < per_sm) per_sm = v;
+    }
     long long grid = (long long)sms * per_sm;
     const long long need = (B + kDenseWarps - 1) / kDenseWarps;
     if (need < grid) grid = need;
