@@ -196,12 +196,11 @@ UVS_DEV void predict_and_A(PBlock& pb, double* Pd, double* At, const double (&h)
         const int d = row / 6, r = row % 6;
         double* pr = Pd + d * kBlkStride + r * 6;
         double v[6];
-        load6(pr, v);
         if (q_identity) {
-#pragma unroll
-            for (int c = 0; c < 6; ++c)
-                if (c == r) { v[c] += 1.0; pr[c] = v[c]; }
+            pr[r] += 1.0;            // one dynamic-address RMW; the row load below is ordered after it (same thread)
+            load6(pr, v);
         } else {
+            load6(pr, v);
 #pragma unroll
             for (int c = 0; c < 6; ++c) { v[c] += __ldg(Qg + (size_t)row * N + 6 * d + c); pr[c] = v[c]; }
         }

@@ -164,7 +164,7 @@ static __device__ __noinline__ void pinv_fallback(int MM, const double* J, const
 // per-group shared scratch; gl = lane index inside the group.  All 32 lanes of the warp must call.
 // Fast path: Cholesky of the smaller Gram matrix (J^T J for M >= 6, J J^T for M < 6) + one step of
 // iterative refinement on the residual (corrected semi-normal equations, error ~ eps cond(J)); if a
-// Cholesky pivot is <= 1e-13 max diag (cond(J) >~ 3e6) group lane 0 runs pinv_fallback.
+// Cholesky pivot is <= 1e-13 trace(Gram) (cond(J) >~ 3e6) group lane 0 runs pinv_fallback.
 // Result in x on every lane of the group.
 template <int M, int GS>
 UVS_DEV void pinv_group(const double* J, double b_lane, double* sc, int gl, double (&x)[6], int& flags) {
@@ -182,8 +182,8 @@ UVS_DEV void pinv_group(const double* J, double b_lane, double* sc, int gl, doub
     if (M >= 6) {
         for (int e = gl; e < 27; e += GS) {
             if (e < 21) {
-                int i = 0;
-                while ((i + 1) * (i + 2) / 2 <= e) ++i;
+                // row of packed-lower entry e < 21, three bits each: 0 1 1 2 2 2 3 3 3 3 4 4 4 4 4 5 5 5 5 5 5
+                const int i = (int)((0x5b6db2491b6d2448ull >> (3 * e)) & 7ull);
                 const int j = e - i * (i + 1) / 2;
                 double s = 0.0;
 #pragma unroll
@@ -211,8 +211,9 @@ UVS_DEV void pinv_group(const double* J, double b_lane, double* sc, int gl, doub
                 L[tri(i, j)] = s;
             }
     }
+    // scale of the rank test: trace(G) (max diag <= trace <= K max diag; a sum is 1 DADD per term where fmax is ~6)
 #pragma unroll
-    for (int i = 0; i < K; ++i) gmax = fmax(gmax, L[tri(i, i)]);
+    for (int i = 0; i < K; ++i) gmax += L[tri(i, i)];
     bool ok = chol_packed<K>(L);
 #pragma unroll
     for (int j = 0; j < K; ++j) {
