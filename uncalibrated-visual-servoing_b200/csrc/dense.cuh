@@ -214,74 +214,177 @@ UVS_DEV void predict_and_A(PBlock& pb, double* Pd, double* At, const double (&h)
 // ---- phase 5: P <- P - L1 R1^T (- L2 R2^T) on the lower blocks ------------------------------------
 // RANK2 = false: P -= Kt^T-rows x Ut^T-rows  (P[i][j] -= sum_k K[i][k] U[j][k])
 // RANK2 = true : P[i][j] -= sum_k K[i][k] V[j][k] + V[i][k] K[j][k]      (V held in Ut)
-template <int M, bool RANK2>
-UVS_DEV void rank_update(PBlock& pb, double* Pd, const double* Kt, const double* Ut, int lane) {
-    constexpr int N = 6 * M, LD = N + 2, NOFF = M * (M - 1) / 2;
-    if (lane < NOFF) {
-        const int bi = pb.bi, bj = pb.bj;
+// Off-diagonal part for k in [K0, K1).  Branch-free: lanes without a block (>= NOFF) carry the dummy block
+// (1, 0) and update registers nobody reads, so the FMAs can be scheduled into a neighbouring dependency chain
+// (see ibvs_with_rank_update) instead of sitting behind a divergent branch.
+template <int M, bool RANK2, int K0, int K1>
+UVS_DEV void rank_update_offdiag(PBlock& pb, const double* Kt, const double* Ut) {
+    constexpr int N = 6 * M, LD = N + 2;
+    const int bi = pb.bi, bj = pb.bj;
 #pragma unroll
-        for (int k = 0; k < M; ++k) {
-            double ki[6], uj[6];
-            load6(Kt + k * LD + 6 * bi, ki);
-            load6(Ut + k * LD + 6 * bj, uj);
+    for (int k = K0; k < K1; ++k) {
+        double ki[6], uj[6];
+        load6(Kt + k * LD + 6 * bi, ki);
+        load6(Ut + k * LD + 6 * bj, uj);
+#pragma unroll
+        for (int r = 0; r < 6; ++r)
+#pragma unroll
+            for (int c = 0; c < 6; ++c) pb.v[r][c] -= ki[r] * uj[c];
+        if (RANK2) {
+            double vi[6], kj[6];
+            load6(Ut + k * LD + 6 * bi, vi);
+            load6(Kt + k * LD + 6 * bj, kj);
 #pragma unroll
             for (int r = 0; r < 6; ++r)
 #pragma unroll
-                for (int c = 0; c < 6; ++c) pb.v[r][c] -= ki[r] * uj[c];
+                for (int c = 0; c < 6; ++c) pb.v[r][c] -= vi[r] * kj[c];
+        }
+    }
+}
+
+// Diagonal blocks: 4 lanes per block.  Lane s owns row rowA = 5 - s (columns 0..rowA) and, for s = 1, 2,
+// row rowB = s - 1 (columns 0..rowB): 6 + 6 + 6 + 3 = 21 lower entries.  All four lanes load the block
+// row's six U values (broadcast) and their own two K values, and run 6 + 2 FMAs per k on fixed
+// registers; entries outside the lane's set are computed and dropped.
+template <int M, bool RANK2>
+UVS_DEV void rank_update_diag(double* Pd, const double* Kt, const double* Ut, int lane) {
+    constexpr int N = 6 * M, LD = N + 2;
+    const int d = lane >> 2, s = lane & 3;
+    if (d < M) {
+        const int rowA = 5 - s;
+        const int rowB = (s == 2) ? 1 : 0;
+        double* pd = Pd + d * kBlkStride;
+        const double* kt = Kt + 6 * d;
+        const double* ut = Ut + 6 * d;
+        double accA[6], accB[2];
+        load6(pd + rowA * 6, accA);
+        accB[0] = pd[rowB * 6]; accB[1] = pd[rowB * 6 + 1];
+#pragma unroll
+        for (int k = 0; k < M; ++k) {
+            double u[6];
+            load6(ut + k * LD, u);
+            const double kA = kt[k * LD + rowA], kB = kt[k * LD + rowB];
+#pragma unroll
+            for (int e = 0; e < 6; ++e) accA[e] -= kA * u[e];
+            accB[0] -= kB * u[0];
+            accB[1] -= kB * u[1];
             if (RANK2) {
-                double vi[6], kj[6];
-                load6(Ut + k * LD + 6 * bi, vi);
-                load6(Kt + k * LD + 6 * bj, kj);
+                double kk[6];
+                load6(kt + k * LD, kk);
+                const double uA = ut[k * LD + rowA], uB = ut[k * LD + rowB];
 #pragma unroll
-                for (int r = 0; r < 6; ++r)
-#pragma unroll
-                    for (int c = 0; c < 6; ++c) pb.v[r][c] -= vi[r] * kj[c];
+                for (int e = 0; e < 6; ++e) accA[e] -= uA * kk[e];
+                accB[0] -= uB * kk[0];
+                accB[1] -= uB * kk[1];
             }
         }
-    }
-    // diagonal blocks: 4 lanes per block.  Lane s owns row rowA = 5 - s (columns 0..rowA) and, for s = 1, 2,
-    // row rowB = s - 1 (columns 0..rowB): 6 + 6 + 6 + 3 = 21 lower entries.  All four lanes load the block
-    // row's six U values (broadcast) and their own two K values, and run 6 + 2 FMAs per k on fixed
-    // registers; entries outside the lane's set are computed and dropped.
-    {
-        const int d = lane >> 2, s = lane & 3;
-        if (d < M) {
-            const int rowA = 5 - s;
-            const int rowB = (s == 2) ? 1 : 0;
-            double* pd = Pd + d * kBlkStride;
-            const double* kt = Kt + 6 * d;
-            const double* ut = Ut + 6 * d;
-            double accA[6], accB[2];
-            load6(pd + rowA * 6, accA);
-            accB[0] = pd[rowB * 6]; accB[1] = pd[rowB * 6 + 1];
 #pragma unroll
-            for (int k = 0; k < M; ++k) {
-                double u[6];
-                load6(ut + k * LD, u);
-                const double kA = kt[k * LD + rowA], kB = kt[k * LD + rowB];
-#pragma unroll
-                for (int e = 0; e < 6; ++e) accA[e] -= kA * u[e];
-                accB[0] -= kB * u[0];
-                accB[1] -= kB * u[1];
-                if (RANK2) {
-                    double kk[6];
-                    load6(kt + k * LD, kk);
-                    const double uA = ut[k * LD + rowA], uB = ut[k * LD + rowB];
-#pragma unroll
-                    for (int e = 0; e < 6; ++e) accA[e] -= uA * kk[e];
-                    accB[0] -= uB * kk[0];
-                    accB[1] -= uB * kk[1];
-                }
-            }
-#pragma unroll
-            for (int e = 0; e < 6; ++e)
-                if (e <= rowA) { pd[rowA * 6 + e] = accA[e]; pd[e * 6 + rowA] = accA[e]; }
-            if (s == 1 || s == 2) {
-                pd[rowB * 6] = accB[0]; pd[rowB] = accB[0];
-                if (s == 2) { pd[rowB * 6 + 1] = accB[1]; pd[6 + rowB] = accB[1]; }
-            }
+        for (int e = 0; e < 6; ++e)
+            if (e <= rowA) { pd[rowA * 6 + e] = accA[e]; pd[e * 6 + rowA] = accA[e]; }
+        if (s == 1 || s == 2) {
+            pd[rowB * 6] = accB[0]; pd[rowB] = accB[0];
+            if (s == 2) { pd[rowB * 6 + 1] = accB[1]; pd[6 + rowB] = accB[1]; }
         }
     }
+}
+
+template <int M, bool RANK2>
+UVS_DEV void rank_update(PBlock& pb, double* Pd, const double* Kt, const double* Ut, int lane) {
+    rank_update_offdiag<M, RANK2, 0, M>(pb, Kt, Ut);
+    rank_update_diag<M, RANK2>(Pd, Kt, Ut, lane);
+}
+
+// IBVS law for M >= 6 (x = pinv(J) b, smallmat.cuh pinv_group with one problem per warp) with the pending
+// covariance update P -= K U^T executed INSIDE it.  The pseudo-inverse is a chain of short dependent stages
+// (Gram entries -> 6x6 Cholesky -> solve -> residual -> solve) that leaves the FP64 pipe mostly idle; the
+// rank-M update is 36 independent FMAs per lane and per k that depend only on K, U (shared memory) and the
+// lane's P block.  Each stage below is one basic block holding both, so the scheduler fills the chain's
+// latency gaps with update FMAs.  Same results as rank_update() followed by pinv_warp().
+template <int M>
+UVS_DEV void ibvs_with_rank_update(PBlock& pb, double* Pd, const double* Kt, const double* Ut, const double* J,
+                                   double b_lane, double* sc, int lane, double (&x)[6], int& flags) {
+    static_assert(M >= 6, "M < 6 uses the J J^T path of pinv_group");
+    constexpr int K = 6;
+    constexpr int C1 = M / 4, C2 = (3 * M) / 4, C3 = M - 1;      // k ranges handed to the four stages
+    double* sG = sc;          // 21
+    double* sg = sc + 21;     // 6
+    double* sb = sc + 27;     // 8
+    double* sr = sc + 35;     // 8
+    double* sx = sc + 43;     // 6
+    __syncwarp();
+    if (lane < M) sb[lane] = b_lane;
+    __syncwarp();
+    // The stages are written branch-free (clamped indices, predicated stores) so that each one stays a single
+    // basic block together with its share of the rank update.
+    {   // stage 1: Gram matrix J^T J (21 entries) and J^T b (6), one per lane: sc[e] = sum_r J[r][i] * q[r]
+        const int e = lane < 27 ? lane : 26;
+        const bool gram = e < 21;
+        const int i = gram ? (int)((0x5b6db2491b6d2448ull >> (3 * e)) & 7ull) : e - 21;
+        const int j = e - i * (i + 1) / 2;
+        const double* q = gram ? J + j : sb;         // second factor: column j of J (stride 6) or b (stride 1)
+        const int qs = gram ? 6 : 1;
+        double s = 0.0;
+#pragma unroll
+        for (int r = 0; r < M; ++r) s += J[r * 6 + i] * q[r * qs];
+        rank_update_offdiag<M, false, 0, C1>(pb, Kt, Ut);
+        if (lane < 27) sc[e] = s;                    // sG = sc[0..21), sg = sc[21..27)
+    }
+    __syncwarp();
+    double L[K * (K + 1) / 2], g[K];
+    bool ok;
+    {   // stage 2: factor, first solve, residual
+#pragma unroll
+        for (int i = 0; i < K * (K + 1) / 2; ++i) L[i] = sG[i];
+#pragma unroll
+        for (int i = 0; i < K; ++i) g[i] = sg[i];
+        double gsum = 0.0;
+#pragma unroll
+        for (int i = 0; i < K; ++i) gsum += L[tri(i, i)];
+        ok = chol_packed<K>(L);
+#pragma unroll
+        for (int j = 0; j < K; ++j) {
+            const double inv = L[tri(j, j)];
+            ok = ok && (inv * inv * gsum * 1e-13 < 1.0);
+        }
+        chol_solve<K>(L, g);
+        const int row = lane < M ? lane : M - 1;
+        double s = sb[row];
+#pragma unroll
+        for (int c = 0; c < 6; ++c) s -= J[row * 6 + c] * g[c];
+        rank_update_offdiag<M, false, C1, C2>(pb, Kt, Ut);
+        if (lane < M) sr[lane] = s;
+    }
+    __syncwarp();
+    {   // stage 3: J^T r
+        const int col = lane < 6 ? lane : 5;
+        double s = 0.0;
+#pragma unroll
+        for (int r = 0; r < M; ++r) s += J[r * 6 + col] * sr[r];
+        rank_update_offdiag<M, false, C2, C3>(pb, Kt, Ut);
+        if (lane < 6) sx[lane] = s;
+    }
+    __syncwarp();
+    {   // stage 4: refinement solve
+        double d[K];
+#pragma unroll
+        for (int i = 0; i < K; ++i) d[i] = sx[i];
+        chol_solve<K>(L, d);
+#pragma unroll
+        for (int i = 0; i < 6; ++i) x[i] = g[i] + d[i];
+        rank_update_offdiag<M, false, C3, M>(pb, Kt, Ut);
+    }
+    rank_update_diag<M, false>(Pd, Kt, Ut, lane);
+    __syncwarp();
+    if (!ok) {
+        flags |= UVS_FLAG_RANK_DEFICIENT;
+        if (lane == 0) pinv_fallback(M, J, sb, sx);
+    }
+    __syncwarp();
+    if (!ok) {
+#pragma unroll
+        for (int i = 0; i < 6; ++i) x[i] = sx[i];
+    }
+    __syncwarp();
 }
 
 // ---- MCKF helpers: block Cholesky of P and the products with it ---------------------------------
@@ -519,11 +622,14 @@ UVS_DEV void chol_solve_sm(const double* Ls, double (&x)[R][M]) {
 struct StepOut {
     int flags = 0;
     int epoch = 0;
+    bool rank_pending = false;
 };
 
 // One predict + update of the filter held in (pb, w).  z_lane: Z_i on lane i < M.  Returns kappa_i on
 // lane i < M (experiment.py:306-308).  K^T is left in w.Kt.
-template <int M, int METHOD>
+// DEFER = true (M >= 6, not MCKF): the covariance update is left pending (out.rank_pending) for the caller to
+// run inside ibvs_with_rank_update(); K^T and U^T stay valid in w.Kt / w.Ut until then.
+template <int M, int METHOD, bool DEFER = false>
 UVS_DEV double dense_step(PBlock& pb, DenseWS<M, METHOD == UVS_METHOD_MCKF>& w, const DenseConsts<M>& cc,
                           const uvs_filter_params& fp, const double (&h)[6], double z_lane, double sigma,
                           int lane, StepOut& out) {
@@ -646,6 +752,7 @@ UVS_DEV double dense_step(PBlock& pb, DenseWS<M, METHOD == UVS_METHOD_MCKF>& w, 
             }
         }
         __syncwarp();
+        if (DEFER) { out.rank_pending = true; return kappa; }
         rank_update<M, false>(pb, w.Pd, w.Kt, w.Ut, lane);
         __syncwarp();
         return kappa;

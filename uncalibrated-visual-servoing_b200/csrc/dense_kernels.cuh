@@ -216,14 +216,21 @@ __global__ void UVS_DENSE_BOUNDS dense_closed_loop_kernel(const __grid_constant_
             {
                 double h[6];                                             // experiment.py:183-188: the previous
                 load6(w.dq, h);                                          // command (zeros on the first frame)
-                kappa = dense_step<M, METHOD>(pb, w, cc, cfg.filt, h, z, sigma, lane, so);
+                kappa = dense_step<M, METHOD, (M >= 6 && !MCKF)>(pb, w, cc, cfg.filt, h, z, sigma, lane, so);
             }
             flags_all |= so.flags;
 
             // IBVS: dq = -gain pinv(J) (kappa o error)                    experiment.py:300-312
             double x[6];
             int ib_flags = 0;
-            pinv_warp<M>(w.X, kappa * (f_l - desired), w.ib, lane, x, ib_flags);
+            if constexpr (M >= 6 && !MCKF) {
+                if (so.rank_pending)
+                    ibvs_with_rank_update<M>(pb, w.Pd, w.Kt, w.Ut, w.X, kappa * (f_l - desired), w.ib, lane, x, ib_flags);
+                else
+                    pinv_warp<M>(w.X, kappa * (f_l - desired), w.ib, lane, x, ib_flags);
+            } else {
+                pinv_warp<M>(w.X, kappa * (f_l - desired), w.ib, lane, x, ib_flags);
+            }
             flags_all |= ib_flags;
             double dq_l = 0.0;
 #pragma unroll
