@@ -250,7 +250,7 @@ template <int M, bool RANK2>
 UVS_DEV void rank_update_diag(double* Pd, const double* Kt, const double* Ut, int lane) {
     constexpr int N = 6 * M, LD = N + 2;
     const int d = lane >> 2, s = lane & 3;
-    if (d < M) {
+    if (M == 8 || d < M) {                     // M = 8: all 32 lanes, no branch
         const int rowA = 5 - s;
         const int rowB = (s == 2) ? 1 : 0;
         double* pd = Pd + d * kBlkStride;
@@ -372,8 +372,8 @@ UVS_DEV void ibvs_with_rank_update(PBlock& pb, double* Pd, const double* Kt, con
 #pragma unroll
         for (int i = 0; i < 6; ++i) x[i] = g[i] + d[i];
         rank_update_offdiag<M, false, C3, M>(pb, Kt, Ut);
+        rank_update_diag<M, false>(Pd, Kt, Ut, lane);
     }
-    rank_update_diag<M, false>(Pd, Kt, Ut, lane);
     __syncwarp();
     if (!ok) {
         flags |= UVS_FLAG_RANK_DEFICIENT;
