@@ -40,7 +40,18 @@ NOISE_SEED, POSE_SEED = 123456, 12345
 M_, N_ = 8, 48
 F_ALG = 4 * N_ ** 2 + 4 * N_ ** 2 * M_ + 4 * N_ * M_ ** 2 + 12 * M_ * N_ + 2 * N_ * M_ + 12 * M_ ** 2 + M_ ** 3 / 3 + 17 * M_
 METRIC = "RMCKF 4-feature closed-loop filter-steps/sec"
+CPU_TRIALS_PER_CORE = 150          # x 300 frames at ~4e3 frames/s/core: 10-15 s of CPU work per sample
 UNIT = "filter-steps/s"
+
+
+def ncu_traffic(kernel):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the bench-sized kernel, from the committed
+    `ncu --set full` capture (profiles/traffic.json, written by tools/profile_summary.py); None when absent."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as fh:
+            return json.load(fh).get(kernel)
+    except (OSError, ValueError):
+        return None
 
 
 def parse():
@@ -99,7 +110,7 @@ def run_reference(a):
     if rank != 0:
         return
     cores = os.cpu_count() or 1
-    tpc = 20
+    tpc = CPU_TRIALS_PER_CORE
     for _ in range(a.warmup):
         cpu_sample(1, cores)
     vals, ms = [], []
@@ -113,7 +124,9 @@ def run_reference(a):
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": a.gpus, "steps": max(1, a.steps),
         "warmup": a.warmup, "ms_per_step": float(np.mean(ms)), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": workload_name("dense (as written)", cores * tpc)},
+        "config": {"workload": workload_name("dense", a.trials), "trials_per_gpu": a.trials, "frames": T_FRAMES,
+                   "sample": f"each step runs {cores * tpc} trials of that workload (bounded CPU sample)",
+                   "noise_seed": NOISE_SEED, "pose_seed": POSE_SEED},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -289,10 +302,12 @@ def run_ours(a):
                    "noise_seed": NOISE_SEED, "pose_seed": POSE_SEED},
         "clocks": clocks.summary(),
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "api": "uvs_closed_loop_host (C ABI, host result buffers)"},
+                "api": "uvs_closed_loop_host (C ABI: configuration struct in, page-locked host result buffers out; "
+                       "scratch allocation, launch, D2H and synchronisation inside the timed region)"},
         "gpu_launches": 2 * a.steps,
         "roofline": {"bound": "fp64", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s",
-                     "frac": achieved / peak_tf, "traffic": None,
+                     "frac": achieved / peak_tf, "traffic": ncu_traffic(f"{a.mode}_closed_loop_kernel<8, GMCKF>"),
+                     "traffic_unit": "bytes per launch (ncu dram read + write); algorithmic: 32 B per trial of results",
                      "kernel": f"{a.mode}_closed_loop_kernel<8, GMCKF>", "kernel_ms": main["kernel_ms"],
                      "flops_per_filter_step_algorithmic": F_ALG,
                      "peak_source": "measured in this run: uvs_fp64_peak (register-resident DFMA chains on every SM); "
@@ -303,9 +318,9 @@ def run_ours(a):
     if extra:
         line["blockdiag"] = extra
     if not a.no_cpu_baseline and world == 1:
-        v, cores, frames, wall = cpu_sample(20)
+        v, cores, frames, wall = cpu_sample(CPU_TRIALS_PER_CORE)
         line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
-                                "sample": f"{cores} processes x 20 closed-loop trials x {T_FRAMES} frames "
+                                "sample": f"{cores} processes x {CPU_TRIALS_PER_CORE} closed-loop trials x {T_FRAMES} frames "
                                           f"(oracle as-written NumPy restatement of experiment.py, 1 BLAS thread each; {wall:.1f} s wall)"}
     print(json.dumps(line), flush=True)
     if world > 1:

@@ -29,7 +29,7 @@ def _deps():
 
 
 def _extra_defs():
-    return [f"-D{k}={os.environ[k]}" for k in ("UVS_DENSE_MINB", "UVS_DENSE_WARPS", "UVS_DENSE_L_SMEM", "UVS_DENSE_MAXNREG") if os.environ.get(k)]
+    return [f"-D{k}={os.environ[k]}" for k in ("UVS_DENSE_MINB", "UVS_DENSE_WARPS", "UVS_DENSE_L_SMEM", "UVS_DENSE_MAXNREG", "UVS_BD_MINB") if os.environ.get(k)]
 
 
 def _compile(src, verbose, tag=""):

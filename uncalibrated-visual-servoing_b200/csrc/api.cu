@@ -224,22 +224,28 @@ int uvs_closed_loop_host(const uvs_closed_loop_cfg* cfg, uint64_t trial0, int64_
                          double* stats_host, int32_t* status_host, int32_t* frames_host) {
     if (!cfg || !stats_host || !status_host || B < 0) return set_error(UVS_ERR_INVALID, "uvs_closed_loop_host: bad argument");
     if (B == 0) return 0;
-    double* d_stats = nullptr;
-    int32_t *d_status = nullptr, *d_frames = nullptr;
-    int rc = check_cuda(cudaMalloc(&d_stats, sizeof(double) * 3 * B), "cudaMalloc stats");
-    if (!rc) rc = check_cuda(cudaMalloc(&d_status, sizeof(int32_t) * B), "cudaMalloc status");
-    if (!rc) rc = check_cuda(cudaMalloc(&d_frames, sizeof(int32_t) * B), "cudaMalloc frames");
-    if (!rc) {
+    // one stream-ordered scratch block (no device-wide synchronisation from cudaMalloc / cudaFree), results copied
+    // straight into the caller's buffers (a DMA when they are page-locked), one stream synchronisation at the end
+    const size_t n_stats = sizeof(double) * 3 * (size_t)B, n_i32 = sizeof(int32_t) * (size_t)B;
+    cudaStream_t st = cudaStreamPerThread;
+    unsigned char* scratch = nullptr;
+    int rc = check_cuda(cudaMallocAsync((void**)&scratch, n_stats + 2 * n_i32, st), "cudaMallocAsync results");
+    if (rc) return rc;
+    double* d_stats = reinterpret_cast<double*>(scratch);
+    int32_t* d_status = reinterpret_cast<int32_t*>(scratch + n_stats);
+    int32_t* d_frames = reinterpret_cast<int32_t*>(scratch + n_stats + n_i32);
+    {
         uvs_closed_loop_io io{};
         io.stats = d_stats; io.status = d_status; io.frames = d_frames;
-        rc = uvs_closed_loop(cfg, trial0, B, &io, nullptr);
+        rc = uvs_closed_loop(cfg, trial0, B, &io, st);
     }
-    if (!rc) rc = check_cuda(cudaMemcpy(stats_host, d_stats, sizeof(double) * 3 * B, cudaMemcpyDeviceToHost), "D2H stats");
-    if (!rc) rc = check_cuda(cudaMemcpy(status_host, d_status, sizeof(int32_t) * B, cudaMemcpyDeviceToHost), "D2H status");
+    if (!rc) rc = check_cuda(cudaMemcpyAsync(stats_host, d_stats, n_stats, cudaMemcpyDeviceToHost, st), "D2H stats");
+    if (!rc) rc = check_cuda(cudaMemcpyAsync(status_host, d_status, n_i32, cudaMemcpyDeviceToHost, st), "D2H status");
     if (!rc && frames_host)
-        rc = check_cuda(cudaMemcpy(frames_host, d_frames, sizeof(int32_t) * B, cudaMemcpyDeviceToHost), "D2H frames");
-    cudaFree(d_stats); cudaFree(d_status); cudaFree(d_frames);
-    return rc;
+        rc = check_cuda(cudaMemcpyAsync(frames_host, d_frames, n_i32, cudaMemcpyDeviceToHost, st), "D2H frames");
+    cudaFreeAsync(scratch, st);
+    const int rc_sync = check_cuda(cudaStreamSynchronize(st), "uvs_closed_loop_host");
+    return rc ? rc : rc_sync;
 }
 
 int uvs_reduce_stats(int64_t B, uint64_t trial0, int32_t sweep_epoch, int32_t n_levels,

@@ -18,6 +18,11 @@
 #include "blockdiag_kernels.h"
 #include "smallmat.cuh"
 
+// resident CTAs per SM asked of ptxas for the closed-loop kernel (register cap 65536 / (MINB * 128))
+#ifndef UVS_BD_MINB
+#define UVS_BD_MINB 2
+#endif
+
 namespace uvs {
 
 template <int GS>
@@ -260,7 +265,7 @@ __global__ void __launch_bounds__(128) bd_replay_kernel(const __grid_constant__ 
 }
 
 template <int M, int METHOD>
-__global__ void __launch_bounds__(128) bd_closed_loop_kernel(const __grid_constant__ ClosedLoopArgs a) {
+__global__ void __launch_bounds__(128, UVS_BD_MINB) bd_closed_loop_kernel(const __grid_constant__ ClosedLoopArgs a) {
     constexpr int GS = GroupSize<M>::value, GPW = 32 / GS, N = 6 * M, LOGW = 6 + 2 * M;
     constexpr int WPC = 4;
     __shared__ __align__(16) double sJ[WPC][GPW][M * 6];
@@ -341,10 +346,13 @@ __global__ void __launch_bounds__(128) bd_closed_loop_kernel(const __grid_consta
         for (int k = 0; k < T; ++k) {
             if (!__any_sync(UVS_FULL_MASK, alive)) break;
             const double t = (double)(k + 1) * cfg.dt;
-            Tf T6;
-            ur10_fk_group<GS>(q, gl, T6);
-            double depth;
-            const double f_true = project_coord(T6, cfg.targets + 3 * (row >> 1), row & 1, depth);
+            // plant: sin/cos of the DH angles split over the group's lanes, then this lane's target point walked
+            // back through the chain into the camera frame (ur10_simulation.py:97-110 + Appendix A pixel model)
+            double sn[6], cs[6], pc[3];
+            ur10_sincos_group<GS>(q, gl, sn, cs);
+            ur10_point_in_camera(sn, cs, cfg.targets + 3 * (row >> 1), pc);
+            const double f_true = pixel_of(pc, row & 1);
+            const double depth = pc[2];
             if (cfg.fov_check) {
                 const bool bad = own && !(f_true >= 0.0 && f_true < kResolution && depth > kMinDepth);
                 if (group_any<GS>(bad) && alive) { alive = false; status = UVS_STATUS_FAIL; flags_all |= UVS_FLAG_OUT_OF_VIEW; }

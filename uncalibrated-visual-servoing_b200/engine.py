@@ -221,12 +221,30 @@ def closed_loop(cfg, trial0, B, *, want_log=False, want_state=False, p_layout=L.
     return out
 
 
-def closed_loop_host(cfg, trial0, B):
-    """The host-buffer entry point: numpy arrays out, synchronous."""
+_pinned = {}
+
+
+def _host_result_buffers(B):
+    """Page-locked result buffers, cached per batch size (pinning is the expensive part), so the device->host
+    copies of ``uvs_closed_loop_host`` are plain DMAs."""
+    if B not in _pinned:
+        _pinned.clear()
+        _pinned[B] = (torch.empty((B, 3), dtype=torch.float64, pin_memory=True),
+                      torch.empty((B,), dtype=torch.int32, pin_memory=True),
+                      torch.empty((B,), dtype=torch.int32, pin_memory=True))
+    return _pinned[B]
+
+
+def closed_loop_host(cfg, trial0, B, pinned=True):
+    """The host-buffer entry point: numpy arrays out, synchronous.  With ``pinned`` the arrays are views of cached
+    page-locked buffers that the next call of the same size overwrites (copy them to keep them)."""
     _require_cuda()
-    stats = np.empty((B, 3), dtype=np.float64)
-    status = np.empty((B,), dtype=np.int32)
-    frames = np.empty((B,), dtype=np.int32)
+    if pinned and B > 0:
+        stats, status, frames = (t.numpy() for t in _host_result_buffers(B))
+    else:
+        stats = np.empty((B, 3), dtype=np.float64)
+        status = np.empty((B,), dtype=np.int32)
+        frames = np.empty((B,), dtype=np.int32)
     L.check(L.load().uvs_closed_loop_host(C.byref(cfg), int(trial0), int(B),
                                           stats.ctypes.data_as(C.POINTER(C.c_double)),
                                           status.ctypes.data_as(C.POINTER(C.c_int32)),
