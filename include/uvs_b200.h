@@ -15,6 +15,8 @@
  *     says "host"; structs are passed by host pointer and read synchronously;
  *   - `stream` is a cudaStream_t passed as void* (NULL = default stream); calls
  *     are asynchronous on it unless stated otherwise;
+ *   - an empty batch (B == 0) is a successful no-op after the scalar arguments have been
+ *     validated; its batch buffers may be NULL (an empty tensor has no storage);
  *   - all arithmetic is IEEE FP64; matrices are row-major and contiguous;
  *   - nf = number of image features (1, 3 or 4); m = 2*nf measurements;
  *     N = 6*m states (the row-major vectorised m x 6 feature Jacobian).

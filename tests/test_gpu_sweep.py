@@ -229,3 +229,63 @@ def test_config4_noise_estimator_sweep(uvs, nf):
         for nname in ("GAUSSIAN_MIXTURE", "ALPHA_STABLE"):
             assert med[(nname, "RMCKF", 10.0)][0] <= 1.05 * med[(nname, "KF", 10.0)][0], (nname, med)
     assert all(v[1] > 0.5 for v in med.values()), med
+
+
+# ------------------------------------------------------------------ empty / ragged / degenerate inputs
+@pytest.mark.parametrize("mode", ["dense", "blockdiag"])
+def test_empty_ragged_and_degenerate_batches(uvs, mode):
+    """B = 0 is a no-op, ragged batch sizes (not a multiple of the warps per CTA / trials per warp) return exactly
+    the rows of a larger launch, T = 1 runs, T = 0 and unknown sizes are argument errors, a NaN start state is a
+    FAIL (experiment.py:313-316) that does not disturb its neighbours."""
+    import torch
+    L, E = uvs._lib, uvs.engine
+    md = L.MODE_DENSE if mode == "dense" else L.MODE_BLOCKDIAG
+    q0 = [0.0, 0.0, 1.96349541, 0.0, -1.57079633, 0.0]
+    des = [149.0, 145.0, 125.0, 121.0, 101.0, 145.0, 125.0, 169.0]
+
+    def cfg(T=300, nf=4, method=5):
+        p = E.filter_params(method, nf, mode=md, annealing=True)
+        return E.closed_loop_cfg(p, E.noise_params(L.NOISE_ALPHA_STABLE, seed=7, alpha=1.4), T=T, dt=0.05, ibvs_gain=0.2,
+                                 q_start=q0, desired_f=des[:2 * nf] if nf == 4 else DESIRED[nf])
+
+    out0 = E.closed_loop(cfg(), 0, 0)
+    assert out0["stats"].shape == (0, 3)
+    big = E.closed_loop(cfg(), 100, 23)
+    torch.cuda.synchronize()
+    bs, bst = big["stats"].cpu().numpy(), big["status"].cpu().numpy()
+    for off, n in ((0, 1), (3, 5), (16, 7), (0, 23)):
+        part = E.closed_loop(cfg(), 100 + off, n)
+        assert np.array_equal(part["stats"].cpu().numpy(), bs[off:off + n])
+        assert np.array_equal(part["status"].cpu().numpy(), bst[off:off + n])
+    one = E.closed_loop(cfg(T=1), 0, 3)
+    assert (one["frames"].cpu().numpy() == 1).all() and np.isfinite(one["stats"].cpu().numpy()).all()
+    with pytest.raises(L.UvsError):
+        E.closed_loop(cfg(T=0), 0, 3)
+    # NaN in one trial's start state: that trial fails, the others are bit-identical to a clean run
+    X0, _ = E.initial_guess(4, E.start_poses(q0, 12345, True, 100, 23))
+    clean = E.closed_loop(cfg(), 100, 23, X0_in=X0)
+    X0n = X0.clone()
+    X0n[4, 7] = float("nan")
+    dirty = E.closed_loop(cfg(), 100, 23, X0_in=X0n)
+    ds, dst = dirty["stats"].cpu().numpy(), dirty["status"].cpu().numpy()
+    assert dst[4] == 1 and (dirty["flags"].cpu().numpy()[4] & L.FLAG_NONFINITE)
+    keep = np.arange(23) != 4
+    assert np.array_equal(ds[keep], clean["stats"].cpu().numpy()[keep])
+    assert np.array_equal(dst[keep], clean["status"].cpu().numpy()[keep])
+    # replay: ragged batch, T = 1; zero-length batch
+    rng = np.random.default_rng(0)
+    for B in (1, 5, 9):
+        f = E.dev(rng.standard_normal((B, 1, 8)) + 128)
+        dq = E.dev(rng.standard_normal((B, 1, 6)) * 0.01)
+        X = E.dev(rng.uniform(size=(B, 48)))
+        p = E.filter_params(2, 4, mode=md)
+        Xo, _, _, fl = E.replay(p, f, dq, E.dev(f[:, 0] * 0 + 128), X, None, p_layout=L.P_BLOCKS)
+        assert Xo.shape == (B, 1, 48) and torch.isfinite(Xo).all()
+        assert torch.equal(Xo[:, 0], X)                          # first frame: H = 0, the state does not move
+    with pytest.raises(L.UvsError):                              # nf must be 1, 3 or 4
+        E.replay(E.filter_params(2, 2, mode=md), E.dev(np.zeros((1, 1, 4))), E.dev(np.zeros((1, 1, 6))),
+                 E.dev(np.zeros((1, 4))), E.dev(np.zeros((1, 24))), None, p_layout=L.P_BLOCKS)
+    # empty batches of the other entry points are no-ops too
+    z = torch.empty((0, 6), dtype=torch.float64, device="cuda")
+    assert E.ur10_fk(z)[0].shape == (0, 4, 4) and E.project(4, z)[0].shape == (0, 8)
+    assert E.noise_fill(E.noise_params(L.NOISE_WHITE, seed=1, std=1.0), 0, 0, 10, 8).shape == (0, 10, 8)

@@ -116,7 +116,7 @@ static int run_replay(ReplayArgs& a, void* stream) {
 int uvs_filter_step(const uvs_filter_params* p, int64_t B, double* X, double* P, int p_layout,
                     const double* h, const double* Z, double sigma,
                     double* K_out, double* kappa_out, int32_t* flags_out, void* stream) {
-    if (!p || !X || !P || !h || !Z) return set_error(UVS_ERR_INVALID, "uvs_filter_step: NULL argument");
+    if (!p || (B > 0 && (!X || !P || !h || !Z))) return set_error(UVS_ERR_INVALID, "uvs_filter_step: NULL argument");
     ReplayArgs a{};
     a.fp = *p; a.B = B; a.T = 1; a.k_max = 1; a.direct = 1; a.p_layout = p_layout; a.sigma = sigma;
     a.h = h; a.Z = Z; a.X = X; a.P = P; a.K_out = K_out; a.kappa_out = kappa_out; a.flags_out = flags_out;
@@ -127,7 +127,7 @@ int uvs_replay(const uvs_filter_params* p, int64_t B, int32_t T, int32_t k_max,
                const double* f, const double* dq, const double* f_init,
                double* X, double* P, int p_layout,
                double* X_out, double* P_out, double* kappa_out, int32_t* flags_out, void* stream) {
-    if (!p || !f || !dq || !f_init || !X) return set_error(UVS_ERR_INVALID, "uvs_replay: NULL argument");
+    if (!p || (B > 0 && (!f || !dq || !f_init || !X))) return set_error(UVS_ERR_INVALID, "uvs_replay: NULL argument");
     ReplayArgs a{};
     a.fp = *p; a.B = B; a.T = T; a.k_max = k_max > 0 ? k_max : T; a.direct = 0; a.p_layout = p_layout;
     a.f = f; a.dq = dq; a.f_init = f_init; a.X = X; a.P = P;
@@ -138,20 +138,20 @@ int uvs_replay(const uvs_filter_params* p, int64_t B, int32_t T, int32_t k_max,
 int uvs_ibvs(int32_t nf, int64_t B, const double* J, const double* e, const double* kappa, double gain,
              double* dq_out, int32_t* flags_out, void* stream) {
     if (!valid_nf(nf)) return set_error(UVS_ERR_INVALID, "nf must be 1, 3 or 4 (got %d)", nf);
-    if (!J || !e || !dq_out || B < 0) return set_error(UVS_ERR_INVALID, "uvs_ibvs: bad argument");
+    if (B < 0 || (B > 0 && (!J || !e || !dq_out))) return set_error(UVS_ERR_INVALID, "uvs_ibvs: bad argument");
     if (B == 0) return 0;
     return check_cuda(launch_ibvs(2 * nf, B, J, e, kappa, gain, dq_out, flags_out, (cudaStream_t)stream), "ibvs");
 }
 
 int uvs_ur10_fk(int64_t B, const double* q, double* T06_out, double* Jgeom_out, void* stream) {
-    if (!q || B < 0) return set_error(UVS_ERR_INVALID, "uvs_ur10_fk: bad argument");
+    if (B < 0 || (B > 0 && !q)) return set_error(UVS_ERR_INVALID, "uvs_ur10_fk: bad argument");
     if (B == 0) return 0;
     return check_cuda(launch_fk(B, q, T06_out, Jgeom_out, (cudaStream_t)stream), "ur10_fk");
 }
 
 int uvs_project(int32_t nf, int64_t B, const double* q, const double* targets_host,
                 double* f_out, double* depth_out, void* stream) {
-    if (!valid_nf(nf) || !q || !targets_host || B < 0) return set_error(UVS_ERR_INVALID, "uvs_project: bad argument");
+    if (!valid_nf(nf) || !targets_host || B < 0 || (B > 0 && !q)) return set_error(UVS_ERR_INVALID, "uvs_project: bad argument");
     if (B == 0) return 0;
     return check_cuda(launch_project(nf, B, q, targets_host, f_out, depth_out, nullptr, (cudaStream_t)stream),
                       "project");
@@ -159,7 +159,7 @@ int uvs_project(int32_t nf, int64_t B, const double* q, const double* targets_ho
 
 int uvs_initial_guess(int32_t nf, int64_t B, const double* q, const double* targets_host,
                       double* X0_out, double* f_out, void* stream) {
-    if (!valid_nf(nf) || !q || !targets_host || !X0_out || B < 0)
+    if (!valid_nf(nf) || !targets_host || B < 0 || (B > 0 && (!q || !X0_out)))
         return set_error(UVS_ERR_INVALID, "uvs_initial_guess: bad argument");
     if (B == 0) return 0;
     return check_cuda(launch_project(nf, B, q, targets_host, f_out, nullptr, X0_out, (cudaStream_t)stream),
@@ -176,7 +176,7 @@ static int check_noise(const uvs_noise_params& np) {
 
 int uvs_noise_fill(const uvs_noise_params* np, uint64_t trial0, int64_t B, int32_t T, int32_t m,
                    double* out, void* stream) {
-    if (!np || !out || B < 0 || T < 0 || m < 2 || (m & 1)) return set_error(UVS_ERR_INVALID, "uvs_noise_fill: bad argument");
+    if (!np || B < 0 || T < 0 || m < 2 || (m & 1) || (B > 0 && T > 0 && !out)) return set_error(UVS_ERR_INVALID, "uvs_noise_fill: bad argument");
     if (int rc = check_noise(*np)) return rc;
     if (B == 0 || T == 0) return 0;
     return check_cuda(launch_noise_fill(*np, trial0, B, T, m, out, (cudaStream_t)stream), "noise_fill");
@@ -184,7 +184,7 @@ int uvs_noise_fill(const uvs_noise_params* np, uint64_t trial0, int64_t B, int32
 
 int uvs_start_poses(const double* q_start_host, uint64_t pose_seed, int32_t change_q_start,
                     uint64_t trial0, int64_t B, double* q_out, void* stream) {
-    if (!q_start_host || !q_out || B < 0) return set_error(UVS_ERR_INVALID, "uvs_start_poses: bad argument");
+    if (!q_start_host || B < 0 || (B > 0 && !q_out)) return set_error(UVS_ERR_INVALID, "uvs_start_poses: bad argument");
     if (B == 0) return 0;
     return check_cuda(launch_start_poses(q_start_host, pose_seed, change_q_start, trial0, B, q_out,
                                          (cudaStream_t)stream), "start_poses");
@@ -192,7 +192,7 @@ int uvs_start_poses(const double* q_start_host, uint64_t pose_seed, int32_t chan
 
 int uvs_closed_loop(const uvs_closed_loop_cfg* cfg, uint64_t trial0, int64_t B,
                     const uvs_closed_loop_io* io, void* stream) {
-    if (!cfg || !io || !io->stats || !io->status) return set_error(UVS_ERR_INVALID, "uvs_closed_loop: NULL argument");
+    if (!cfg || !io || (B > 0 && (!io->stats || !io->status))) return set_error(UVS_ERR_INVALID, "uvs_closed_loop: NULL argument");
     const uvs_filter_params& fp = cfg->filt;
     if (!valid_nf(fp.nf)) return set_error(UVS_ERR_INVALID, "nf must be 1, 3 or 4 (got %d)", fp.nf);
     if (!valid_method(fp.method)) return set_error(UVS_ERR_INVALID, "method %d is not a filter method", fp.method);
@@ -222,7 +222,7 @@ int uvs_closed_loop(const uvs_closed_loop_cfg* cfg, uint64_t trial0, int64_t B,
 
 int uvs_closed_loop_host(const uvs_closed_loop_cfg* cfg, uint64_t trial0, int64_t B,
                          double* stats_host, int32_t* status_host, int32_t* frames_host) {
-    if (!cfg || !stats_host || !status_host || B < 0) return set_error(UVS_ERR_INVALID, "uvs_closed_loop_host: bad argument");
+    if (!cfg || B < 0 || (B > 0 && (!stats_host || !status_host))) return set_error(UVS_ERR_INVALID, "uvs_closed_loop_host: bad argument");
     if (B == 0) return 0;
     // one stream-ordered scratch block (no device-wide synchronisation from cudaMalloc / cudaFree), results copied
     // straight into the caller's buffers (a DMA when they are page-locked), one stream synchronisation at the end
@@ -250,7 +250,7 @@ int uvs_closed_loop_host(const uvs_closed_loop_cfg* cfg, uint64_t trial0, int64_
 
 int uvs_reduce_stats(int64_t B, uint64_t trial0, int32_t sweep_epoch, int32_t n_levels,
                      const double* stats, const int32_t* status, double* sums, double* n_fail, void* stream) {
-    if (!stats || !status || !sums || !n_fail || B < 0 || n_levels < 1 || n_levels > 4096)
+    if (!sums || !n_fail || B < 0 || n_levels < 1 || n_levels > 4096 || (B > 0 && (!stats || !status)))
         return set_error(UVS_ERR_INVALID, "uvs_reduce_stats: bad argument");
     if (B == 0) return 0;
     return check_cuda(launch_reduce_stats(B, trial0, sweep_epoch, n_levels, stats, status, sums, n_fail,
