@@ -144,6 +144,12 @@ def test_kinematics_match_oracle(uvs):
     for b in range(len(q)):
         assert np.allclose(T06[b], K.fkine(q[b]), rtol=0, atol=1e-13)
         assert np.allclose(Jg[b], K.jacobian(q[b]), rtol=0, atol=1e-13)
+    # many turns of every joint (range reduction of the in-kernel sincos) and a diverged pose (its slow path)
+    qw = rng.uniform(-60.0, 60.0, size=(64, 6))
+    qw[1] *= 1e4
+    Tw = E.ur10_fk(E.dev(qw), want_jacobian=False)[0].cpu().numpy()
+    for b in range(len(qw)):
+        assert np.allclose(Tw[b], K.fkine(qw[b]), rtol=0, atol=2e-13 if b != 1 else 1e-9)
     for nf in (1, 3, 4):
         f, depth = E.project(nf, E.dev(q))
         X0, f2 = E.initial_guess(nf, E.dev(q))
