@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define UVS_ABI_VERSION 1
+#define UVS_ABI_VERSION 2
 
 /* experiment.py:6-11 (Method).  RMCKF is the paper's name for GMCKF. */
 enum { UVS_METHOD_ANALYTICAL = 1, UVS_METHOD_KF = 2, UVS_METHOD_MCKF = 3,
@@ -133,6 +133,28 @@ typedef struct uvs_closed_loop_io {
     int32_t reserved;
 } uvs_closed_loop_io;
 
+/* The camera-twist pipeline of the reference's tests/ scripts (tests/{ibvs,kalman,mckf}_{1,3,4}_feature(s).py):
+ * the filter regresses the feature differences on the commanded camera twist dp, the control law
+ * produces dp = -GAIN pinv(J)(f - f*), and the joints follow dq = pinv(J_geom) kron(I2, R06^T) dp
+ * (kalman_4_features.py:152-173).  GAIN, TS, T, q_start, desired_f, targets, noise and the filter
+ * parameters are the uvs_closed_loop_cfg fields (ibvs_gain, dt, ...); this block adds what only the scripts have. */
+enum { UVS_X0_ZEROS = 0,            /* X = 0 (kalman_1_feature.py:44); first f_old = 0               */
+       UVS_X0_IMAGE_JACOBIAN = 1,   /* X = analytic interaction matrix at the start pose, first f_old =
+                                       the noise-free features (kalman_4_features.py:74-101)         */
+       UVS_X0_RANDOM = 2 };         /* X ~ U(0,1)^N from Philox (kalman_3_features.py:50); f_old = 0 */
+enum { UVS_DEPTH_DISTANCE = 0,      /* Z_i = |camera - disc_i| (computeZ, ur10_simulation.py:170-195) */
+       UVS_DEPTH_HEIGHT = 1 };      /* Z = T06[2][3] (getCameraHeight, ibvs_1_feature.py:58)          */
+
+typedef struct uvs_twist_cfg {
+    int32_t x0_mode;         /* UVS_X0_*; io->X0_in replaces the state but not the first f_old     */
+    int32_t depth_mode;      /* UVS_DEPTH_* used by the interaction matrix                        */
+    int32_t dp_zero_mask;    /* bit i set: dp[i] = 0 after the control law (kalman_3_features.py:139-141) */
+    int32_t reserved;
+    double focal_x0;         /* focal length of the initial guess (kalman_4_features.py:85: 1024)  */
+    double focal;            /* focal length of the UVS_METHOD_ANALYTICAL interaction matrix (ibvs_4_features.py:81) */
+    double err_threshold;    /* frames run while ||f - f*||_2 > err_threshold (kalman_4_features.py:111); < 0: all T */
+} uvs_twist_cfg;
+
 /* library / error plumbing */
 int uvs_version(void);
 int uvs_last_error(char* buf, size_t n);
@@ -192,6 +214,12 @@ int uvs_start_poses(const double* q_start_host, uint64_t pose_seed, int32_t chan
  * with the simulator replaced by the kinematic UR10 + pinhole model. */
 int uvs_closed_loop(const uvs_closed_loop_cfg* cfg, uint64_t trial0, int64_t B,
                     const uvs_closed_loop_io* io, void* stream);
+
+/* B trials of the tests/-style camera-twist loop (see uvs_twist_cfg).  cfg->filt.method may be
+ * UVS_METHOD_ANALYTICAL (tests/ibvs_*.py) or any filter; general covariance (dense family) only.
+ * io as for uvs_closed_loop; stats use t_k = (k+1) dt; frames[b] < T when the threshold stopped the trial. */
+int uvs_twist_loop(const uvs_closed_loop_cfg* cfg, const uvs_twist_cfg* tw, uint64_t trial0, int64_t B,
+                   const uvs_closed_loop_io* io, void* stream);
 
 /* Same with HOST result buffers (stats_host [B,3], status_host [B],
  * frames_host [B]); allocates scratch, runs, copies back, synchronises. */

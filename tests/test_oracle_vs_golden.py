@@ -144,3 +144,62 @@ def test_closed_loop_statistics_match_reference():
             ks = sps.ks_2samp(mine[:, j], g["stats"][:, j])
             assert ks.pvalue > 1e-3, (name, j, ks)
         assert abs(np.median(mine[:, 2]) / np.median(g["stats"][:, 2]) - 1) < 0.15
+
+
+# ---- camera-twist pipeline: the oracle against the reference's own tests/ scripts -----------------------------
+TWIST_SCRIPTS = ["ibvs_1_feature", "ibvs_3_features", "ibvs_4_features", "kalman_1_feature", "kalman_3_features",
+                 "kalman_4_features", "mckf_1_feature", "mckf_3_features", "mckf_4_features"]
+
+
+def twist_cfg_from_golden(g):
+    """The oracle configuration stored beside a ref_twist_*.npz golden (oracle/make_golden_twist.py)."""
+    from oracle import twist_loop
+    kw = {}
+    for key in g["cfg_keys"]:
+        v = g["cfg_" + str(key)]
+        key = str(key)
+        if key in ("method", "x0_mode", "depth_mode", "dp_zero_mask", "fpi_epoch_max"):
+            kw[key] = int(v)
+        elif key in ("joseph", "mckf_skip", "square_inv"):
+            kw[key] = bool(v)
+        elif key == "desired_f":
+            kw[key] = [float(x) for x in v]
+        else:
+            kw[key] = float(v)
+    kw["desired_f"] = [float(x) for x in g["desired_f"]]
+    return twist_loop.make_cfg(nf=int(g["nf"]), T=int(g["T"]), dt=float(g["dt"]), **kw)
+
+
+@pytest.mark.parametrize("name", TWIST_SCRIPTS)
+def test_twist_loop_matches_reference_scripts(name):
+    """oracle/twist_loop.py reproduces what /root/reference/tests/<name>.py computed (executed unmodified against the
+    stubbed simulator): joint and feature trajectories every frame, the final state and covariance."""
+    from oracle import twist_loop
+    g = load_golden(f"ref_twist_{name}.npz")
+    cfg = twist_cfg_from_golden(g)
+    assert cfg["gain"] == float(g["gain"])
+    T, k = int(g["T"]), int(g["frames"])
+    noise = np.zeros((T, 2 * int(g["nf"])))
+    noise[:k] = g["noise_log"]
+    res = twist_loop.run_trial(cfg, 0, noise=noise, x0=g.get("x0"), record=True)
+    assert res["frames"] == k
+    assert np.abs(res["q_log"] - g["q_log"]).max() <= 1e-12
+    assert rel_err(res["f_log"], g["f_log"]) <= 1e-12
+    assert np.abs(res["q_final"] - g["q_final"]).max() <= 1e-12
+    if "X_final" in g:
+        assert rel_err(res["X"], g["X_final"]) <= 1e-12
+        assert rel_err(res["P"], g["P_final"]) <= 1e-12
+    if "X_log" in g:
+        assert rel_err(res["X_log"], g["X_log"]) <= 1e-12
+
+
+def test_twist_loop_threshold_stops_the_trial():
+    """kalman_4_features.py:111 — the loop ends on the first frame whose PREVIOUS error norm is <= the threshold."""
+    from oracle import twist_loop
+    g = load_golden("ref_twist_ibvs_4_features.npz")
+    cfg = twist_cfg_from_golden(g)
+    cfg["err_threshold"] = 2.5            # below ||ones(8)|| = 2.83 (the scripts' initial error), above the final 2.28
+    res = twist_loop.run_trial(cfg, 0, noise=np.zeros((int(g["T"]), 8)))
+    err = np.linalg.norm(res["f_log"] - np.asarray(cfg["desired_f"]), axis=1)
+    assert 1 < res["frames"] < int(g["T"])
+    assert err[-1] <= 2.5 and np.all(err[:-1] > 2.5)

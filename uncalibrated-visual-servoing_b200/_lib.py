@@ -19,6 +19,9 @@ P_DENSE, P_BLOCKS = 0, 1
 FLAG_SKIP_SINGULAR, FLAG_SKIP_MAXEPOCH, FLAG_CX_SINGULAR, FLAG_NOT_SPD = 1, 2, 4, 8
 FLAG_RANK_DEFICIENT, FLAG_NONFINITE, FLAG_OUT_OF_VIEW = 16, 32, 64
 FLAG_EPOCH_SHIFT = 8
+# tests/-script pipeline (uvs_twist_cfg)
+X0_ZEROS, X0_IMAGE_JACOBIAN, X0_RANDOM = 0, 1, 2
+DEPTH_DISTANCE, DEPTH_HEIGHT = 0, 1
 
 _dp = C.c_void_p
 
@@ -51,6 +54,12 @@ class ClosedLoopIO(C.Structure):
                 ("reserved", C.c_int32)]
 
 
+class TwistCfg(C.Structure):
+    _fields_ = [("x0_mode", C.c_int32), ("depth_mode", C.c_int32), ("dp_zero_mask", C.c_int32),
+                ("reserved", C.c_int32), ("focal_x0", C.c_double), ("focal", C.c_double),
+                ("err_threshold", C.c_double)]
+
+
 _PROTOTYPES = {
     "uvs_version": ([], C.c_int),
     "uvs_last_error": ([C.c_char_p, C.c_size_t], C.c_int),
@@ -66,6 +75,8 @@ _PROTOTYPES = {
     "uvs_noise_fill": ([C.POINTER(NoiseParams), C.c_uint64, C.c_int64, C.c_int32, C.c_int32, _dp, _dp], C.c_int),
     "uvs_start_poses": ([C.POINTER(C.c_double), C.c_uint64, C.c_int32, C.c_uint64, C.c_int64, _dp, _dp], C.c_int),
     "uvs_closed_loop": ([C.POINTER(ClosedLoopCfg), C.c_uint64, C.c_int64, C.POINTER(ClosedLoopIO), _dp], C.c_int),
+    "uvs_twist_loop": ([C.POINTER(ClosedLoopCfg), C.POINTER(TwistCfg), C.c_uint64, C.c_int64, C.POINTER(ClosedLoopIO),
+                        _dp], C.c_int),
     "uvs_closed_loop_host": ([C.POINTER(ClosedLoopCfg), C.c_uint64, C.c_int64, C.POINTER(C.c_double),
                               C.POINTER(C.c_int32), C.POINTER(C.c_int32)], C.c_int),
     "uvs_reduce_stats": ([C.c_int64, C.c_uint64, C.c_int32, C.c_int32, _dp, _dp, _dp, _dp, _dp], C.c_int),

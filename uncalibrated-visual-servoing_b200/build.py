@@ -16,7 +16,8 @@ CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(HERE, "build")
 # tuning builds: UVS_DENSE_MINB=<n> python build.py --out libuvs_b200_minb<n>.so ; select with UVS_B200_LIB=<path>
 LIB = os.path.join(HERE, "libuvs_b200.so")
-SOURCES = ["api.cu", "aux_kernels.cu", "blockdiag_kernels.cu", "dense_m2.cu", "dense_m6.cu", "dense_m8.cu"]
+SOURCES = ["api.cu", "aux_kernels.cu", "blockdiag_kernels.cu", "dense_m2.cu", "dense_m6.cu", "dense_m8.cu",
+           "twist_m2.cu", "twist_m6.cu", "twist_m8.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
          "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", "--expt-relaxed-constexpr",
@@ -54,7 +55,7 @@ def build(force=False, verbose=False, out=None):
         newest = max(os.path.getmtime(p) for p in _deps())
         if os.path.getmtime(lib) >= newest:
             return lib
-    with cf.ThreadPoolExecutor(max_workers=min(8, len(SOURCES))) as ex:
+    with cf.ThreadPoolExecutor(max_workers=min(os.cpu_count() or 4, len(SOURCES))) as ex:
         objs = list(ex.map(lambda s: _compile(s, verbose, tag), SOURCES))
     cmd = [NVCC, "-shared", "-o", lib] + objs + ["-gencode", "arch=compute_100a,code=sm_100a", "-cudart", "static"]
     r = subprocess.run(cmd, capture_output=True, text=True)

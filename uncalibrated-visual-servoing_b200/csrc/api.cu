@@ -7,6 +7,7 @@
 #include "aux_kernels.h"
 #include "blockdiag_kernels.h"
 #include "dense_kernels.cuh"
+#include "twist_kernels.cuh"
 
 namespace uvs {
 
@@ -218,6 +219,39 @@ int uvs_closed_loop(const uvs_closed_loop_cfg* cfg, uint64_t trial0, int64_t B,
     default: e = launch_dense_closed_loop<8>(a, d.sms, st); break;
     }
     return check_cuda(e, "dense closed-loop launch");
+}
+
+int uvs_twist_loop(const uvs_closed_loop_cfg* cfg, const uvs_twist_cfg* tw, uint64_t trial0, int64_t B,
+                   const uvs_closed_loop_io* io, void* stream) {
+    if (!cfg || !tw || !io || (B > 0 && (!io->stats || !io->status))) return set_error(UVS_ERR_INVALID, "uvs_twist_loop: NULL argument");
+    const uvs_filter_params& fp = cfg->filt;
+    if (!valid_nf(fp.nf)) return set_error(UVS_ERR_INVALID, "nf must be 1, 3 or 4 (got %d)", fp.nf);
+    if (fp.method != UVS_METHOD_ANALYTICAL && !valid_method(fp.method)) return set_error(UVS_ERR_INVALID, "method %d", fp.method);
+    if (cfg->T < 1 || B < 0) return set_error(UVS_ERR_INVALID, "T=%d B=%lld", cfg->T, (long long)B);
+    if (cfg->sweep_len < 0 || cfg->sweep_len > UVS_MAX_SWEEP) return set_error(UVS_ERR_INVALID, "sweep_len");
+    if (tw->x0_mode < UVS_X0_ZEROS || tw->x0_mode > UVS_X0_RANDOM) return set_error(UVS_ERR_INVALID, "x0_mode %d", tw->x0_mode);
+    if (tw->depth_mode != UVS_DEPTH_DISTANCE && tw->depth_mode != UVS_DEPTH_HEIGHT) return set_error(UVS_ERR_INVALID, "depth_mode %d", tw->depth_mode);
+    if (tw->dp_zero_mask < 0 || tw->dp_zero_mask > 63) return set_error(UVS_ERR_INVALID, "dp_zero_mask %d", tw->dp_zero_mask);
+    if ((fp.method == UVS_METHOD_ANALYTICAL && !(tw->focal > 0.0)) ||
+        (tw->x0_mode == UVS_X0_IMAGE_JACOBIAN && !(tw->focal_x0 > 0.0)))
+        return set_error(UVS_ERR_INVALID, "focal lengths must be positive");
+    if (!fp.joseph && fp.method == UVS_METHOD_MCKF)
+        return set_error(UVS_ERR_UNSUPPORTED, "MCKF requires the Joseph update");
+    if (fp.mode == UVS_MODE_BLOCKDIAG) return set_error(UVS_ERR_UNSUPPORTED, "the twist loop runs in the dense family only");
+    if (int rc = check_noise(cfg->noise)) return rc;
+    if (B == 0) return 0;
+    DeviceInfo d;
+    if (int rc = device_info(d)) return rc;
+    TwistArgs a{};
+    a.cfg = *cfg; a.tw = *tw; a.io = *io; a.trial0 = trial0; a.B = B;
+    cudaStream_t st = (cudaStream_t)stream;
+    cudaError_t e;
+    switch (2 * fp.nf) {
+    case 2: e = launch_twist_loop<2>(a, d.sms, st); break;
+    case 6: e = launch_twist_loop<6>(a, d.sms, st); break;
+    default: e = launch_twist_loop<8>(a, d.sms, st); break;
+    }
+    return check_cuda(e, "twist loop launch");
 }
 
 int uvs_closed_loop_host(const uvs_closed_loop_cfg* cfg, uint64_t trial0, int64_t B,

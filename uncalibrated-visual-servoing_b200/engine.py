@@ -221,6 +221,44 @@ def closed_loop(cfg, trial0, B, *, want_log=False, want_state=False, p_layout=L.
     return out
 
 
+def twist_cfg(*, x0_mode=L.X0_IMAGE_JACOBIAN, depth_mode=L.DEPTH_DISTANCE, dp_zero_mask=0, focal_x0=1024.0,
+              focal=200.91975387103875, err_threshold=-1.0):
+    """The parameters only the reference's tests/ scripts have (include/uvs_b200.h: uvs_twist_cfg)."""
+    tw = L.TwistCfg()
+    tw.x0_mode, tw.depth_mode, tw.dp_zero_mask = int(x0_mode), int(depth_mode), int(dp_zero_mask)
+    tw.focal_x0, tw.focal, tw.err_threshold = float(focal_x0), float(focal), float(err_threshold)
+    return tw
+
+
+def twist_loop(cfg, tw, trial0, B, *, want_log=False, want_state=False, p_layout=L.P_DENSE, noise_in=None,
+               q0_in=None, X0_in=None, device="cuda", out=None):
+    """B trials of the tests/-style camera-twist loop (tests/{ibvs,kalman,mckf}_*.py); same outputs as
+    ``closed_loop``.  cfg.ibvs_gain is the scripts' GAIN, cfg.dt their TS."""
+    _require_cuda()
+    m = 2 * cfg.filt.nf
+    N = 6 * m
+    if out is None:
+        out = dict(stats=torch.empty((B, 3), dtype=torch.float64, device=device),
+                   status=torch.empty((B,), dtype=torch.int32, device=device),
+                   frames=torch.empty((B,), dtype=torch.int32, device=device),
+                   flags=torch.empty((B,), dtype=torch.int32, device=device))
+        if want_log:
+            out["log"] = torch.zeros((B, cfg.T, 6 + 2 * m), dtype=torch.float64, device=device)
+        if want_state:
+            out["X"] = torch.empty((B, N), dtype=torch.float64, device=device)
+            shape = (B, N, N) if p_layout == L.P_DENSE else (B, m, 6, 6)
+            out["P"] = torch.zeros(shape, dtype=torch.float64, device=device)
+    io = L.ClosedLoopIO()
+    io.stats, io.status = _ptr(out["stats"]).value, _ptr(out["status"]).value
+    io.frames, io.flags = _ptr(out.get("frames")).value, _ptr(out.get("flags")).value
+    io.log, io.X_out, io.P_out = _ptr(out.get("log")).value, _ptr(out.get("X")).value, _ptr(out.get("P")).value
+    io.noise_in, io.q0_in, io.X0_in = _ptr(noise_in).value, _ptr(q0_in).value, _ptr(X0_in).value
+    io.p_layout = int(p_layout)
+    L.check(L.load().uvs_twist_loop(C.byref(cfg), C.byref(tw), int(trial0), int(B), C.byref(io), _stream()),
+            "uvs_twist_loop")
+    return out
+
+
 _pinned = {}
 
 
