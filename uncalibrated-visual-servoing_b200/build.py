@@ -30,7 +30,9 @@ def _deps():
 
 
 def _extra_defs():
-    return [f"-D{k}={os.environ[k]}" for k in ("UVS_DENSE_MINB", "UVS_DENSE_WARPS", "UVS_DENSE_L_SMEM", "UVS_DENSE_MAXNREG", "UVS_BD_MINB") if os.environ.get(k)]
+    names = ["UVS_DENSE_MINB", "UVS_DENSE_WARPS", "UVS_DENSE_L_SMEM", "UVS_DENSE_MAXNREG", "UVS_BD_MINB", "UVS_DENSE_FAST"]
+    names += sorted(k for k in os.environ if k.startswith("UVS_OPT_"))
+    return [f"-D{k}={os.environ[k]}" for k in names if os.environ.get(k)]
 
 
 def _compile(src, verbose, tag=""):

@@ -543,11 +543,11 @@ template <int M>
 UVS_DEV bool build_and_factor_S(const double* Ain, const double (&h)[6], const DenseConsts<M>& cc,
                                 double w_lane, bool plain_R, double s0_scale, double* Ssm, double* wsm,
                                 double* Dsm, double* ddiag, int d_mode, double dscale,
-                                double (&L)[M * (M + 1) / 2], int lane) {
+                                double (&L)[M * (M + 1) / 2], int lane, bool r_id) {
     constexpr int N = 6 * M, LD = N + 2;
     if (lane < M) {
         wsm[lane] = w_lane;
-        if (d_mode != 0 && cc.r_identity) ddiag[lane] = (d_mode == 1) ? w_lane - 1.0 : dscale;
+        if (d_mode != 0 && r_id) ddiag[lane] = (d_mode == 1) ? w_lane - 1.0 : dscale;
     }
     __syncwarp();
     for (int e = lane; e < M * M; e += 32) {
@@ -558,15 +558,15 @@ UVS_DEV bool build_and_factor_S(const double* Ain, const double (&h)[6], const D
 #pragma unroll
         for (int r = 0; r < 6; ++r) s0 += h[r] * a[r];
         double rh;
-        if (plain_R) rh = cc.R[e];
-        else if (cc.r_identity) rh = (i == k) ? wsm[i] : 0.0;
+        if (plain_R) rh = r_id ? ((i == k) ? 1.0 : 0.0) : cc.R[e];
+        else if (r_id) rh = (i == k) ? wsm[i] : 0.0;
         else {
             rh = 0.0;
 #pragma unroll
             for (int j = 0; j < M; ++j) rh += cc.Br[i * M + j] * wsm[j] * cc.Br[k * M + j];
         }
         Ssm[e] = s0_scale * s0 + rh;
-        if (!cc.r_identity) {
+        if (!r_id) {
             if (d_mode == 1) Dsm[e] = rh - cc.R[e];
             else if (d_mode == 2) Dsm[e] = dscale * cc.R[e];
         }
@@ -629,12 +629,16 @@ struct StepOut {
 // lane i < M (experiment.py:306-308).  K^T is left in w.Kt.
 // DEFER = true (M >= 6, not MCKF): the covariance update is left pending (out.rank_pending) for the caller to
 // run inside ibvs_with_rank_update(); K^T and U^T stay valid in w.Kt / w.Ut until then.
-template <int M, int METHOD, bool DEFER = false>
+// FAST = true: Q = I, R = I and the Joseph form are compile-time facts (the reference's hard-coded
+// experiment.py:73-76,297), so the general-Q/R code and its warp-uniform branches are not in the frame loop.
+template <int M, int METHOD, bool DEFER = false, bool FAST = false>
 UVS_DEV double dense_step(PBlock& pb, DenseWS<M, METHOD == UVS_METHOD_MCKF>& w, const DenseConsts<M>& cc,
                           const uvs_filter_params& fp, const double (&h)[6], double z_lane, double sigma,
                           int lane, StepOut& out) {
     constexpr int N = 6 * M, LD = N + 2;
-    predict_and_A<M>(pb, w.Pd, w.At, h, fp.Q, cc.q_identity, lane);
+    const bool r_id = FAST || (cc.r_identity != 0);
+    const bool joseph = FAST || (fp.joseph != 0);
+    predict_and_A<M>(pb, w.Pd, w.At, h, fp.Q, FAST ? 1 : cc.q_identity, lane);
 
     // innovation nu = Z - H X (lane i < M), published through shared memory
     double nu_l = 0.0;
@@ -650,7 +654,7 @@ UVS_DEV double dense_step(PBlock& pb, DenseWS<M, METHOD == UVS_METHOD_MCKF>& w, 
     // whitened innovation e = Br^-1 nu
     double e_l = 0.0;
     if (lane < M) {
-        if (cc.r_identity) e_l = nu_l;
+        if (r_id) e_l = nu_l;
         else {
 #pragma unroll
             for (int j = 0; j < M; ++j) e_l += cc.Brinv[lane * M + j] * w.nu[j];
@@ -669,18 +673,18 @@ UVS_DEV double dense_step(PBlock& pb, DenseWS<M, METHOD == UVS_METHOD_MCKF>& w, 
             kappa = c;
             w_lane = 1.0 / (c + 1e-6);                                             // experiment.py:280
             plain_R = false;
-            d_mode = fp.joseph ? 1 : 0;
+            d_mode = joseph ? 1 : 0;
         } else if (METHOD == UVS_METHOD_IMCCKF) {
             double q = 0.0;                                                        // experiment.py:258-261
 #pragma unroll
             for (int j = 0; j < M; ++j) { const double ej = shfl_d(e_l, j); q += ej * ej; }
             const double c = gaussian_kernel(sqrt(q), sigma);
             s0_scale = c; gain_scale = c; dscale = 1.0 - c;
-            d_mode = fp.joseph ? 2 : 0;
+            d_mode = joseph ? 2 : 0;
         }
         double* ddiag = w.ib + 8;
         const bool ok = build_and_factor_S<M>(w.At, h, cc, w_lane, plain_R, s0_scale, w.S, w.ib, w.D, ddiag, d_mode,
-                                              dscale, L, lane);
+                                              dscale, L, lane, r_id);
         if (!ok) {                       // S not SPD: skip the correction, P keeps +Q
             out.flags |= UVS_FLAG_NOT_SPD;
             for (int e = lane; e < M * LD; e += 32) w.Kt[e] = 0.0;
@@ -688,7 +692,7 @@ UVS_DEV double dense_step(PBlock& pb, DenseWS<M, METHOD == UVS_METHOD_MCKF>& w, 
             return kappa;
         }
         const bool use_D = d_mode != 0;
-        const bool diag_D = cc.r_identity != 0;
+        const bool diag_D = r_id;
 #if UVS_DENSE_L_SMEM
         {   // every lane holds the same factor: publish it once, then let the registers go
             constexpr int NL = M * (M + 1) / 2;
@@ -809,7 +813,7 @@ UVS_DEV double dense_step(PBlock& pb, DenseWS<M, METHOD == UVS_METHOD_MCKF>& w, 
                 for (int r = 0; r < 6; ++r) r_l -= h[r] * w.Xc[6 * lane + r];
             }
             double ey = 0.0;
-            if (cc.r_identity) ey = r_l;
+            if (r_id) ey = r_l;
             else {
 #pragma unroll
                 for (int j = 0; j < M; ++j) { const double rj = shfl_d(r_l, j); if (lane < M) ey += cc.Brinv[lane * M + j] * rj; }
@@ -818,7 +822,7 @@ UVS_DEV double dense_step(PBlock& pb, DenseWS<M, METHOD == UVS_METHOD_MCKF>& w, 
             if (__any_sync(UVS_FULL_MASK, cy == 0.0)) {                 // experiment.py:231-236
                 out.flags |= UVS_FLAG_SKIP_SINGULAR; skip = true; break;
             }
-            const bool ok = build_and_factor_S<M>(Ain, h, cc, 1.0 / cy, false, 1.0, w.S, w.ib, nullptr, nullptr, 0, 0.0, L, lane);
+            const bool ok = build_and_factor_S<M>(Ain, h, cc, 1.0 / cy, false, 1.0, w.S, w.ib, nullptr, nullptr, 0, 0.0, L, lane, r_id);
             if (!ok) { out.flags |= UVS_FLAG_NOT_SPD; skip = true; break; }
             // K rows, X_corrected = X + K (Z - H X)        experiment.py:238-242
             double num = 0.0, den = 0.0;
@@ -856,7 +860,7 @@ UVS_DEV double dense_step(PBlock& pb, DenseWS<M, METHOD == UVS_METHOD_MCKF>& w, 
             for (int k = 0; k < M; ++k) {
                 double v = w.At[k * LD + row];
 #pragma unroll
-                for (int j = 0; j < M; ++j) v -= 0.5 * kr[j] * (w.D[j * M + k] + cc.R[j * M + k]);
+                for (int j = 0; j < M; ++j) v -= 0.5 * kr[j] * (w.D[j * M + k] + (r_id ? (j == k ? 1.0 : 0.0) : cc.R[j * M + k]));
                 w.Ut[k * LD + row] = v;
             }
         }

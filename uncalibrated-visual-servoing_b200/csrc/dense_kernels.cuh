@@ -12,6 +12,10 @@
 #ifndef UVS_DENSE_MINB
 #define UVS_DENSE_MINB 2
 #endif
+// 1: closed-loop launches with Q = R = NULL and the Joseph form use the instantiation that knows it at compile time
+#ifndef UVS_DENSE_FAST
+#define UVS_DENSE_FAST 1
+#endif
 
 #ifdef UVS_DENSE_MAXNREG
 #define UVS_DENSE_BOUNDS __maxnreg__(UVS_DENSE_MAXNREG)
@@ -85,7 +89,8 @@ __global__ void UVS_DENSE_BOUNDS dense_replay_kernel(const __grid_constant__ Rep
     }
 }
 
-template <int M, int METHOD>
+// FAST: Q = R = NULL (identity) and the Joseph update, known at compile time (dense_step<..., FAST>).
+template <int M, int METHOD, bool FAST>
 __global__ void UVS_DENSE_BOUNDS dense_closed_loop_kernel(const __grid_constant__ ClosedLoopArgs a) {
     constexpr int N = 6 * M;
     constexpr bool MCKF = METHOD == UVS_METHOD_MCKF;
@@ -216,7 +221,7 @@ __global__ void UVS_DENSE_BOUNDS dense_closed_loop_kernel(const __grid_constant_
             {
                 double h[6];                                             // experiment.py:183-188: the previous
                 load6(w.dq, h);                                          // command (zeros on the first frame)
-                kappa = dense_step<M, METHOD, (M >= 6 && !MCKF)>(pb, w, cc, cfg.filt, h, z, sigma, lane, so);
+                kappa = dense_step<M, METHOD, (M >= 6 && !MCKF), FAST>(pb, w, cc, cfg.filt, h, z, sigma, lane, so);
             }
             flags_all |= so.flags;
 
@@ -309,7 +314,11 @@ static cudaError_t dense_launch(Kernel kernel, const Args& a, long long B, size_
                             dense_smem_bytes<MM, METHOD == UVS_METHOD_MCKF>(kDenseWarps), sms, st);          \
     }                                                                                                        \
     template <int METHOD> static cudaError_t closed_one_##MM(const ClosedLoopArgs& a, int sms, cudaStream_t st) { \
-        return dense_launch(dense_closed_loop_kernel<MM, METHOD>, a, a.B,                                    \
+        const uvs_filter_params& fp = a.cfg.filt;                                                            \
+        if (UVS_DENSE_FAST && fp.Q == nullptr && fp.R == nullptr && fp.joseph)                               \
+            return dense_launch(dense_closed_loop_kernel<MM, METHOD, UVS_DENSE_FAST != 0>, a, a.B,           \
+                                dense_smem_bytes<MM, METHOD == UVS_METHOD_MCKF>(kDenseWarps), sms, st);      \
+        return dense_launch(dense_closed_loop_kernel<MM, METHOD, false>, a, a.B,                             \
                             dense_smem_bytes<MM, METHOD == UVS_METHOD_MCKF>(kDenseWarps), sms, st);          \
     }                                                                                                        \
     template <> cudaError_t launch_dense_replay<MM>(const ReplayArgs& a, int sms, cudaStream_t st) {         \
