@@ -634,7 +634,7 @@ struct StepOut {
 template <int M, int METHOD, bool DEFER = false, bool FAST = false>
 UVS_DEV double dense_step(PBlock& pb, DenseWS<M, METHOD == UVS_METHOD_MCKF>& w, const DenseConsts<M>& cc,
                           const uvs_filter_params& fp, const double (&h)[6], double z_lane, double sigma,
-                          int lane, StepOut& out) {
+                          int lane, StepOut& out, double inv_s2 = 0.0) {
     constexpr int N = 6 * M, LD = N + 2;
     const bool r_id = FAST || (cc.r_identity != 0);
     const bool joseph = FAST || (fp.joseph != 0);
@@ -669,9 +669,12 @@ UVS_DEV double dense_step(PBlock& pb, DenseWS<M, METHOD == UVS_METHOD_MCKF>& w, 
         double s0_scale = 1.0, w_lane = 1.0;
         int d_mode = 0;
         if (METHOD == UVS_METHOD_GMCKF) {
-            const double c = (lane < M) ? gaussian_kernel(e_l, sigma) : 1.0;      // experiment.py:274-276
+            // experiment.py:274-276, 280.  FAST (closed loop): the caller supplies 1 / sigma^2 from its per-CTA table, the
+            // weight is exp(-(e^2 / 2) (1 / sigma^2)) (argument within 1 ulp of utils.py:171-172's) and 1 / (c + 1e-6)
+            // is the branch-free reciprocal (c + 1e-6 lies in [1e-6, 1.000001])
+            const double c = (lane < M) ? (FAST ? exp(-0.5 * (e_l * e_l) * inv_s2) : gaussian_kernel(e_l, sigma)) : 1.0;
             kappa = c;
-            w_lane = 1.0 / (c + 1e-6);                                             // experiment.py:280
+            w_lane = FAST ? fast_div(1.0, c + 1e-6) : 1.0 / (c + 1e-6);
             plain_R = false;
             d_mode = joseph ? 1 : 0;
         } else if (METHOD == UVS_METHOD_IMCCKF) {

@@ -36,6 +36,13 @@ __host__ __device__ constexpr size_t dense_smem_bytes(int warps) {
     return sizeof(DenseConsts<M>) + (size_t)warps * sizeof(DenseWS<M, MCKF>);
 }
 
+// closed loop: per-CTA table {sigma_k, 1 / sigma_k^2} of the annealed kernel bandwidth (experiment.py:196-199), filled
+// once per CTA with the IEEE division instead of once per trial and frame; trials longer than this fall back to it
+constexpr int kSigmaTableMax = 1024;
+__host__ __device__ constexpr size_t sigma_table_bytes(int T) {
+    return (T <= kSigmaTableMax) ? (size_t)T * 2 * sizeof(double) : 0;
+}
+
 template <int M, int METHOD>
 __global__ void UVS_DENSE_BOUNDS dense_replay_kernel(const __grid_constant__ ReplayArgs a) {
     constexpr int N = 6 * M;
@@ -100,10 +107,19 @@ __global__ void UVS_DENSE_BOUNDS dense_closed_loop_kernel(const __grid_constant_
     DenseWS<M, MCKF>* wsv = reinterpret_cast<DenseWS<M, MCKF>*>(smem_raw + sizeof(DenseConsts<M>));
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpc = blockDim.x >> 5;
     const uvs_closed_loop_cfg& cfg = a.cfg;
+    const int T = cfg.T;
+    const double2* sig_tab = nullptr;
+    if (sigma_table_bytes(T) != 0) {
+        double2* tab = reinterpret_cast<double2*>(smem_raw + sizeof(DenseConsts<M>) + (size_t)wpc * sizeof(DenseWS<M, MCKF>));
+        for (int k = threadIdx.x; k < T; k += blockDim.x) {
+            const double sg = annealed_bw(cfg.filt.kernel_bw, cfg.filt.annealing, k, T);
+            tab[k] = make_double2(sg, 1.0 / (sg * sg));
+        }
+        sig_tab = tab;
+    }
     if (threadIdx.x == 0) init_consts<M>(cc, cfg.filt);
     __syncthreads();
     DenseWS<M, MCKF>& w = wsv[warp];
-    const int T = cfg.T;
 
     for (long long b = (long long)blockIdx.x * wpc + warp; b < a.B; b += (long long)gridDim.x * wpc) {
         const uint64_t trial = a.trial0 + (uint64_t)b;
@@ -178,7 +194,7 @@ __global__ void UVS_DENSE_BOUNDS dense_closed_loop_kernel(const __grid_constant_
             if (lane < 6) {
                 q_l = w.q[lane];
                 double sn, cs;
-                sincos(dh_theta(lane, q_l), &sn, &cs);
+                sincos_bounded(dh_theta(lane, q_l), &sn, &cs);
                 *reinterpret_cast<double2*>(w.sc + 2 * lane) = make_double2(sn, cs);
             }
             __syncwarp();
@@ -191,7 +207,7 @@ __global__ void UVS_DENSE_BOUNDS dense_closed_loop_kernel(const __grid_constant_
                     sn[j] = t.x; cs[j] = t.y;
                 }
                 ur10_point_in_camera(sn, cs, target, pc);
-                f_true = pixel_of(pc, lane & 1);
+                f_true = kPrincipal + fast_div(kFocal * ((lane & 1) ? pc[1] : pc[0]), pc[2]);    // pixel_of()
                 depth = pc[2];
             }
             if (cfg.fov_check) {
@@ -215,13 +231,15 @@ __global__ void UVS_DENSE_BOUNDS dense_closed_loop_kernel(const __grid_constant_
             const double f_new = f_true + nz;                            // experiment.py:130-135
             const double z = f_new - f_l;                                // experiment.py:170-177
             f_l = f_new;
-            const double sigma = annealed_bw(cfg.filt.kernel_bw, cfg.filt.annealing, k, T);
+            double sigma, inv_s2;
+            if (sig_tab) { const double2 t = sig_tab[k]; sigma = t.x; inv_s2 = t.y; }
+            else { sigma = annealed_bw(cfg.filt.kernel_bw, cfg.filt.annealing, k, T); inv_s2 = 1.0 / (sigma * sigma); }
             StepOut so;
             double kappa;
             {
                 double h[6];                                             // experiment.py:183-188: the previous
                 load6(w.dq, h);                                          // command (zeros on the first frame)
-                kappa = dense_step<M, METHOD, (M >= 6 && !MCKF), FAST>(pb, w, cc, cfg.filt, h, z, sigma, lane, so);
+                kappa = dense_step<M, METHOD, (M >= 6 && !MCKF), FAST>(pb, w, cc, cfg.filt, h, z, sigma, lane, so, inv_s2);
             }
             flags_all |= so.flags;
 
@@ -317,9 +335,11 @@ static cudaError_t dense_launch(Kernel kernel, const Args& a, long long B, size_
         const uvs_filter_params& fp = a.cfg.filt;                                                            \
         if (UVS_DENSE_FAST && fp.Q == nullptr && fp.R == nullptr && fp.joseph)                               \
             return dense_launch(dense_closed_loop_kernel<MM, METHOD, UVS_DENSE_FAST != 0>, a, a.B,           \
-                                dense_smem_bytes<MM, METHOD == UVS_METHOD_MCKF>(kDenseWarps), sms, st);      \
+                                dense_smem_bytes<MM, METHOD == UVS_METHOD_MCKF>(kDenseWarps) +               \
+                                    sigma_table_bytes(a.cfg.T), sms, st);                                    \
         return dense_launch(dense_closed_loop_kernel<MM, METHOD, false>, a, a.B,                             \
-                            dense_smem_bytes<MM, METHOD == UVS_METHOD_MCKF>(kDenseWarps), sms, st);          \
+                            dense_smem_bytes<MM, METHOD == UVS_METHOD_MCKF>(kDenseWarps) +                   \
+                                sigma_table_bytes(a.cfg.T), sms, st);                                        \
     }                                                                                                        \
     template <> cudaError_t launch_dense_replay<MM>(const ReplayArgs& a, int sms, cudaStream_t st) {         \
         switch (a.fp.method) {                                                                               \
