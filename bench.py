@@ -13,7 +13,7 @@ is one frame of one trial; only frames actually executed are counted.
 
 Prints ONE JSON line (rank 0).  `value` is timed with CUDA events with everything resident on
 the device; `e2e` goes through the host-buffer C-ABI entry point (uvs_closed_loop_host: scratch
-allocation, launch, D2H of the results) per step.
+launch, D2H of the results, synchronisation) per step.
 """
 import argparse
 import json
@@ -302,8 +302,8 @@ def run_ours(a):
                    "noise_seed": NOISE_SEED, "pose_seed": POSE_SEED},
         "clocks": clocks.summary(),
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "api": "uvs_closed_loop_host (C ABI: configuration struct in, page-locked host result buffers out; "
-                       "scratch allocation, launch, D2H and synchronisation inside the timed region)"},
+                "api": "uvs_closed_loop_host (C ABI: configuration struct in by host pointer, page-locked host result "
+                       "buffers out; launch, D2H of the per-trial results and stream synchronisation inside the timed region)"},
         "gpu_launches": 2 * a.steps,
         "roofline": {"bound": "fp64", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s",
                      "frac": achieved / peak_tf, "traffic": ncu_traffic(f"{a.mode}_closed_loop_kernel<8, GMCKF>"),

@@ -258,13 +258,26 @@ int uvs_closed_loop_host(const uvs_closed_loop_cfg* cfg, uint64_t trial0, int64_
                          double* stats_host, int32_t* status_host, int32_t* frames_host) {
     if (!cfg || B < 0 || (B > 0 && (!stats_host || !status_host))) return set_error(UVS_ERR_INVALID, "uvs_closed_loop_host: bad argument");
     if (B == 0) return 0;
-    // one stream-ordered scratch block (no device-wide synchronisation from cudaMalloc / cudaFree), results copied
-    // straight into the caller's buffers (a DMA when they are page-locked), one stream synchronisation at the end
+    // results land in a per-host-thread device scratch block that only grows (a stream-ordered cudaMallocAsync /
+    // cudaFreeAsync pair per call was measured to stall for up to 1.8 s when the pool hands memory back to the driver
+    // at the synchronisation point), are copied straight into the caller's buffers (a DMA when they are page-locked)
+    // and the call ends with one stream synchronisation
     const size_t n_stats = sizeof(double) * 3 * (size_t)B, n_i32 = sizeof(int32_t) * (size_t)B;
     cudaStream_t st = cudaStreamPerThread;
-    unsigned char* scratch = nullptr;
-    int rc = check_cuda(cudaMallocAsync((void**)&scratch, n_stats + 2 * n_i32, st), "cudaMallocAsync results");
+    struct Scratch { unsigned char* p = nullptr; size_t cap = 0; int dev = -1; };
+    static thread_local Scratch sc;
+    int dev = 0;
+    int rc = check_cuda(cudaGetDevice(&dev), "cudaGetDevice");
     if (rc) return rc;
+    if (sc.dev != dev || sc.cap < n_stats + 2 * n_i32) {
+        if (sc.p && sc.dev == dev) cudaFree(sc.p);
+        sc = Scratch{};
+        rc = check_cuda(cudaMalloc((void**)&sc.p, n_stats + 2 * n_i32), "cudaMalloc result scratch");
+        if (rc) { sc = Scratch{}; return rc; }
+        sc.cap = n_stats + 2 * n_i32;
+        sc.dev = dev;
+    }
+    unsigned char* scratch = sc.p;
     double* d_stats = reinterpret_cast<double*>(scratch);
     int32_t* d_status = reinterpret_cast<int32_t*>(scratch + n_stats);
     int32_t* d_frames = reinterpret_cast<int32_t*>(scratch + n_stats + n_i32);
@@ -277,7 +290,6 @@ int uvs_closed_loop_host(const uvs_closed_loop_cfg* cfg, uint64_t trial0, int64_
     if (!rc) rc = check_cuda(cudaMemcpyAsync(status_host, d_status, n_i32, cudaMemcpyDeviceToHost, st), "D2H status");
     if (!rc && frames_host)
         rc = check_cuda(cudaMemcpyAsync(frames_host, d_frames, n_i32, cudaMemcpyDeviceToHost, st), "D2H frames");
-    cudaFreeAsync(scratch, st);
     const int rc_sync = check_cuda(cudaStreamSynchronize(st), "uvs_closed_loop_host");
     return rc ? rc : rc_sync;
 }

@@ -77,9 +77,14 @@ UVS_DEV double noise_sample(const uvs_noise_params& np, double sweep_rho, double
             if (beta == 0.0) {
                 // sin(aV) / cos(V)^(1/a) * (cos((1-a)V) / W)^((1-a)/a), powers through exp/log (all
                 // bases are positive here): ~2x cheaper than two pow() calls, relative error < 1e-14
+                // The three angles lie in (-pi, pi): the bounded sincos (common.cuh) replaces sin / cos / cos, and
+                // log(cos((1-a)V)) - log(W) is one logarithm of the branch-free quotient (both positive, tame).
                 const double ia = 1.0 / alpha;
-                value = sin(alpha * V) *
-                        exp((1.0 - alpha) * ia * (log(cos(V * (1.0 - alpha))) - log(W)) - ia * log(cos(V)));
+                double s_av, c_av, s_bv, c_bv, s_v, c_v;
+                sincos_bounded(alpha * V, &s_av, &c_av);
+                sincos_bounded(V * (1.0 - alpha), &s_bv, &c_bv);
+                sincos_bounded(V, &s_v, &c_v);
+                value = s_av * exp((1.0 - alpha) * ia * log(fast_div(c_bv, W)) - ia * log(c_v));
             } else if (alpha != 1.0) {
                 const double constant = beta * tan(M_PI * alpha / 2);
                 const double Bc = atan(constant);
