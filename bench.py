@@ -12,7 +12,7 @@ per-level statistics reduction, + the NCCL all-reduce of those sums when N > 1).
 is one frame of one trial; only frames actually executed are counted.
 
 Prints ONE JSON line (rank 0).  `value` is timed with CUDA events with everything resident on
-the device; `e2e` goes through the host-buffer C-ABI entry point (uvs_closed_loop_host: scratch
+the device; `e2e` goes through the host-buffer C-ABI entry point (uvs_closed_loop_host:
 launch, D2H of the results, synchronisation) per step.
 """
 import argparse
@@ -64,6 +64,7 @@ def parse():
     ap.add_argument("--trials", type=int, default=100_000, help="trials per GPU per step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-blockdiag-extra", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the trajectory-logging and camera-twist legs")
     return ap.parse_args()
 
 
@@ -253,7 +254,7 @@ def run_ours(a):
         main = timed(a.mode, a.steps, a.warmup)
     value = main["frames"] * a.steps / (main["ms_total"] * 1e-3)
 
-    # end-to-end through the host-buffer C-ABI entry point (per step: scratch alloc, launch, D2H, sync)
+    # end-to-end through the host-buffer C-ABI entry point (per step: launch, D2H, sync)
     cfg = make_cfg(a.mode)
     E.closed_loop_host(cfg, trial0, B)       # warm-up at the timed size: page-locked result buffers, stream-ordered pool
     torch.cuda.synchronize()
@@ -284,6 +285,50 @@ def run_ours(a):
                  "note": "block-diagonal family (exact for the reference's P0=Q=I, R=I); its own executed flops "
                          "are ~5e3 per step, never multiplied by F_alg"}
 
+    # trajectory logging (experiment.py:323-330: q, f, noise per frame = 22 doubles at 4 features): the same launch with
+    # the [B,T,22] log enabled, its HBM write rate beside the measured copy bandwidth
+    logging = twist = None
+    if not a.no_extras and a.mode == "dense" and rank == 0:
+        Bl = min(B, 50_000)
+        cfgl = make_cfg("dense")
+        outl = E.closed_loop(cfgl, trial0, Bl, want_log=True)
+        torch.cuda.synchronize()
+        l0, l1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        flush.fill_(0.0)
+        l0.record()
+        E.closed_loop(cfgl, trial0, Bl, out=outl)
+        l1.record()
+        torch.cuda.synchronize()
+        ms = l0.elapsed_time(l1)
+        fr = int(outl["frames"].sum().item())
+        log_bytes = fr * (6 + 2 * M_) * 8
+        peaks = {}
+        try:
+            with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as fh:
+                peaks = json.load(fh)
+        except (OSError, ValueError):
+            pass
+        logging = {"value": fr / (ms * 1e-3), "unit": UNIT, "trials": Bl, "log_bytes_per_filter_step": (6 + 2 * M_) * 8,
+                   "hbm_write_gbs": log_bytes / (ms * 1e-3) / 1e9, "hbm_peak_gbs": peaks.get("hbm_gbs"),
+                   "note": "dense closed loop with the per-frame trajectory log (q, f, noise) written to HBM"}
+        del outl
+        # camera-twist pipeline of the reference's tests/ scripts (kalman_4_features.py configuration, white noise)
+        pt = E.filter_params(L.METHOD_KF, 4, mode=L.MODE_DENSE)
+        cfgt = E.closed_loop_cfg(pt, E.noise_params(L.NOISE_WHITE, seed=NOISE_SEED, std=1.0), T=440, dt=DT, ibvs_gain=0.5,
+                                 q_start=[0.0, -np.pi / 8, np.pi / 2 + np.pi / 8, 0.0, -np.pi / 2, 0.0],
+                                 desired_f=DESIRED_F, change_q_start=False)
+        tw = E.twist_cfg(x0_mode=L.X0_IMAGE_JACOBIAN, focal_x0=1024.0, err_threshold=0.01)
+        Bt = 20_000
+        outt = E.twist_loop(cfgt, tw, 0, Bt)
+        torch.cuda.synchronize()
+        l0.record()
+        E.twist_loop(cfgt, tw, 0, Bt, out=outt)
+        l1.record()
+        torch.cuda.synchronize()
+        twist = {"value": int(outt["frames"].sum().item()) / (l0.elapsed_time(l1) * 1e-3), "unit": UNIT, "trials": Bt,
+                 "note": "uvs_twist_loop: tests/kalman_4_features.py pipeline (KF on the camera twist, pinv(J_geom) "
+                         "joint rates), 440 frames, white noise"}
+
     peak_tf, _ = E.fp64_peak(4096)
     peak_tf = max(peak_tf, E.fp64_peak(4096)[0])
     if rank != 0:
@@ -304,7 +349,7 @@ def run_ours(a):
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "api": "uvs_closed_loop_host (C ABI: configuration struct in by host pointer, page-locked host result "
                        "buffers out; launch, D2H of the per-trial results and stream synchronisation inside the timed region)"},
-        "gpu_launches": 2 * a.steps,
+        "gpu_launches": 2 * a.steps,      # per step: the closed-loop kernel + the statistics reduction
         "roofline": {"bound": "fp64", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s",
                      "frac": achieved / peak_tf, "traffic": ncu_traffic(f"{a.mode}_closed_loop_kernel<8, GMCKF>"),
                      "traffic_unit": "bytes per launch (ncu dram read + write); algorithmic: 32 B per trial of results",
@@ -317,6 +362,10 @@ def run_ours(a):
     }
     if extra:
         line["blockdiag"] = extra
+    if logging:
+        line["logging"] = logging
+    if twist:
+        line["twist"] = twist
     if not a.no_cpu_baseline and world == 1:
         v, cores, frames, wall = cpu_sample(CPU_TRIALS_PER_CORE)
         line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",

@@ -9,5 +9,5 @@ import json;d=json.load(open("$O/bench.json"));print("dense",d["value"],"frac",d
 PY
 if [ -n "$NCU" ]; then
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:dense_closed_loop -c 1 -o $O/dense_full -f \
-    python bench.py --steps 1 --warmup 1 --trials 14800 --no-cpu-baseline --no-blockdiag-extra > $O/ncu_dense.log 2>&1
+    python bench.py --steps 1 --warmup 1 --trials 14800 --no-cpu-baseline --no-blockdiag-extra --no-extras > $O/ncu_dense.log 2>&1
 fi
