@@ -90,7 +90,7 @@ def main():
         cubin = [f for f in os.listdir(cub) if f.startswith("dense_m8")]
         if cubin:
             out = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "ncu_by_line.py"), sass,
-                                  os.path.join(cub, cubin[0]), "dense_closed_loop_kernelILi8ELi5", "40"],
+                                  os.path.join(cub, cubin[0]), "dense_closed_loop_kernelILi8ELi5ELb1", "40"],
                                  capture_output=True, text=True).stdout
             with open(os.path.join(dst, f"{label}_dense_by_line.txt"), "w") as fh:
                 fh.write(out)
