@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define UVS_ABI_VERSION 2
+#define UVS_ABI_VERSION 3
 
 /* experiment.py:6-11 (Method).  RMCKF is the paper's name for GMCKF. */
 enum { UVS_METHOD_ANALYTICAL = 1, UVS_METHOD_KF = 2, UVS_METHOD_MCKF = 3,
@@ -115,6 +115,12 @@ typedef struct uvs_closed_loop_cfg {
     uint64_t pose_seed;      /* Philox key of the start-pose draws (config experiments.seed) */
     double sweep[UVS_MAX_SWEEP];
     const double* P0;        /* device [N,N] or NULL = identity (experiment.py:73)         */
+    /* joint servo limits of the scenes (position-controlled joints, Ruc v_max = 1.0472 rad/s,
+     * a_max = 6.283 rad/s^2); 0 = unlimited = the kinematic plant q <- q + dq dt of experiment.py:320,335.
+     * Per frame: v = clamp(dq, v_prev -+ a_max dt) ; v = clamp(v, -+v_max) ; q += v dt ; v_prev = v.
+     * The filter regressor stays the COMMANDED dq, as in the reference (experiment.py:188). */
+    double v_max;
+    double a_max;
 } uvs_closed_loop_cfg;
 
 /* buffers of a closed-loop batch; any optional pointer may be NULL */

@@ -23,6 +23,7 @@ DEFAULTS = dict(
     noise_params=dict(alpha=1.5, beta=0.0, gamma=1.0, delta=0.0),
     hold_cnt=0, noise_seed=123456, pose_seed=12345, change_q_start=True,
     fov_check=False, P0=None, Q=None, R=None, targets=None, structured=False,
+    v_max=0.0, a_max=0.0,        # joint servo limits (SURVEY.md Appendix A 'Joints'); 0 = kinematic plant
 )
 
 
@@ -30,6 +31,18 @@ def make_cfg(**kw):
     cfg = dict(DEFAULTS)
     cfg.update(kw)
     return cfg
+
+
+def servo_rate(cfg, dq, v_prev):
+    """Joint rates actually executed for the commanded dq under the scene's servo limits
+    (include/uvs_b200.h: uvs_closed_loop_cfg.v_max / a_max): acceleration clamp, then velocity clamp."""
+    v = np.array(dq, dtype=float)
+    if cfg.get("a_max", 0.0) > 0.0:
+        dv = cfg["a_max"] * cfg["dt"]
+        v = np.minimum(np.maximum(v, v_prev - dv), v_prev + dv)
+    if cfg.get("v_max", 0.0) > 0.0:
+        v = np.minimum(np.maximum(v, -cfg["v_max"]), cfg["v_max"])
+    return v
 
 
 def in_view(f, z):
@@ -81,6 +94,7 @@ def run_trial(cfg, trial, noise=None, q0=None, x0=None, record=False):
     flags_log = np.zeros(T, dtype=np.int64); epoch_log = np.zeros(T, dtype=np.int64)
     status = SUCCESS
     dq = np.zeros(6)
+    v_prev = np.zeros(6)
     k = 0
     for k_it in range(T):
         t = (k_it + 1) * dt
@@ -116,7 +130,8 @@ def run_trial(cfg, trial, noise=None, q0=None, x0=None, record=False):
             X_log[k] = X
             P_log.append(Pb.copy() if structured else P.copy())
         k += 1
-        q = q + dq * dt                                           # experiment.py:320,335
+        v_prev = servo_rate(cfg, dq, v_prev)
+        q = q + v_prev * dt                                       # experiment.py:320,335 (v = dq without limits)
     out = dict(status=status, frames=k, q_log=q_log[:k], f_log=f_log[:k], noise_log=noise_log[:k],
                t_log=t_log[:k], kernel_bw_log=bw_log[:k], dq_log=dq_log[:k],
                flags_log=flags_log[:k], epoch_log=epoch_log[:k], X=X,

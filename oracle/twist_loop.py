@@ -21,7 +21,7 @@ Pinned against the unmodified scripts executed with a stubbed simulator: oracle/
 """
 import numpy as np
 
-from . import filters, kinematics, noise_model, stats as stats_mod
+from . import closed_loop, filters, kinematics, noise_model, stats as stats_mod
 
 SUCCESS, FAIL = 0, 1
 DEPTH_DISTANCE, DEPTH_HEIGHT = 0, 1          # computeZ (ur10_simulation.py:170-195) / getCameraHeight (:146-149)
@@ -36,6 +36,7 @@ DEFAULTS = dict(
     kernel_bw=20.0, fpi_threshold=0.01, fpi_epoch_max=100, annealing=False, joseph=True, mckf_skip=False,
     noise_type=0, noise_params={}, hold_cnt=0,
     noise_seed=123456, pose_seed=12345, change_q_start=False, targets=None, P0=None, Q=None, R=None,
+    v_max=0.0, a_max=0.0,
 )
 
 
@@ -115,6 +116,7 @@ def run_trial(cfg, trial=0, noise=None, q0=None, x0=None, record=False):
     X_log = np.zeros((T, N)) if record else None
     status = SUCCESS
     dp = np.zeros(6)
+    v_prev = np.zeros(6)
     error = np.ones(m)                                       # kalman_4_features.py:70
     k = 0
     for k_it in range(T):
@@ -154,7 +156,8 @@ def run_trial(cfg, trial=0, noise=None, q0=None, x0=None, record=False):
         if record:
             X_log[k] = X
         k += 1
-        q = q + dq * dt
+        v_prev = closed_loop.servo_rate(cfg, dq, v_prev)
+        q = q + v_prev * dt
     out = dict(status=status, frames=k, q_log=q_log[:k], f_log=f_log[:k], noise_log=noise_log[:k],
                t_log=t_log[:k], dp_log=dp_log[:k], dq_log=dq_log[:k], X=X, P=P, q_final=q)
     out["stats"] = stats_mod.trial_stats(out["t_log"], out["f_log"], desired)

@@ -477,3 +477,40 @@ def test_experiment_api_drop_in(uvs):
     with pytest.raises(NotImplementedError):
         uvs.Experiment(g["q_start"], exp.desired_f, None, 0.05, 15, 0.2, None, uvs.Method.ANALYTICAL,
                        method_params=dict(initial_guess=True))
+
+
+@pytest.mark.parametrize("limits", [dict(v_max=0.2), dict(a_max=6.283), dict(v_max=0.3, a_max=2.0)],
+                         ids=["vmax", "amax", "both"])
+def test_servo_limits_match_oracle(uvs, limits):
+    """SURVEY §8f row 3 (first step): the scenes' joint servo limits (Appendix A: 60 deg/s, 360 deg/s^2) as an
+    acceleration + velocity clamp on the executed joint rate, both kernel families against the oracle."""
+    from oracle import closed_loop as CL, noise_model as NM
+    L, E = uvs._lib, uvs.engine
+    B, trial0 = 4, 50
+    npar = dict(alpha=1.3, beta=0.0, gamma=1.0, delta=0.0)
+    ocfg = CL.make_cfg(method=METHODS["GMCKF"], annealing=True, noise_type=NM.ALPHA_STABLE, noise_params=npar,
+                       noise_seed=77, pose_seed=5, **limits)
+    ref = [CL.run_trial(ocfg, trial0 + b) for b in range(B)]
+    free = CL.run_trial(CL.make_cfg(method=METHODS["GMCKF"], annealing=True, noise_type=NM.ALPHA_STABLE,
+                                    noise_params=npar, noise_seed=77, pose_seed=5), trial0)
+    assert np.abs(free["q_log"] - ref[0]["q_log"]).max() > 1e-3            # the limits actually bite
+    if "v_max" in limits:
+        for r in ref:
+            assert np.abs(np.diff(r["q_log"], axis=0)).max() <= limits["v_max"] * 0.05 * (1 + 1e-12)
+    for mode in (L.MODE_DENSE, L.MODE_BLOCKDIAG):
+        p = E.filter_params(METHODS["GMCKF"], 4, mode=mode, annealing=True)
+        cfg = E.closed_loop_cfg(p, E.noise_params(NM.ALPHA_STABLE, seed=77, **npar), T=300, dt=0.05, ibvs_gain=0.2,
+                                q_start=ocfg["q_start"], desired_f=ocfg["desired_f"], pose_seed=5, **limits)
+        out = E.closed_loop(cfg, trial0, B, want_log=True)
+        log, st = out["log"].cpu().numpy(), out["stats"].cpu().numpy()
+        for b in range(B):
+            n = tame_prefix(ref[b]["dq_log"])
+            assert n >= 5
+            assert rel_err(log[b, :n, 0:6], ref[b]["q_log"][:n]) <= 1e-6, (mode, b)
+            assert rel_err(log[b, :n, 6:14], ref[b]["f_log"][:n]) <= 1e-6, (mode, b)
+            if n == ref[b]["frames"]:
+                assert rel_err(st[b], ref[b]["stats"]) <= 1e-6, (mode, b)
+    bad = E.closed_loop_cfg(E.filter_params(5, 4), E.noise_params(0), T=5, dt=0.05, ibvs_gain=0.2, q_start=ocfg["q_start"],
+                            desired_f=ocfg["desired_f"], v_max=-1.0)
+    with pytest.raises(L.UvsError):
+        E.closed_loop(bad, 0, 1)

@@ -179,3 +179,20 @@ def test_twist_loop_argument_errors_and_batch_invariance(uvs):
                              desired_f=ocfg["desired_f"])
     with pytest.raises(L.UvsError):
         E.twist_loop(cfg2, tw, 0, 1)
+
+
+def test_twist_loop_servo_limits(uvs):
+    """The joint servo limits apply to the twist pipeline's plant too (executed rate = clamp of pinv(J_geom) dx)."""
+    from oracle import twist_loop
+    L, E = uvs._lib, uvs.engine
+    ocfg = twist_loop.make_cfg(method=2, nf=4, T=150, gain=0.5, noise_type=1, noise_params=dict(std=1.0), v_max=0.05, a_max=0.5)
+    cfg, tw = gpu_cfg(uvs, ocfg, noise=_noise_params(uvs, ocfg))
+    cfg.v_max, cfg.a_max = ocfg["v_max"], ocfg["a_max"]
+    out = E.twist_loop(cfg, tw, 3, 2, want_log=True)
+    log = out["log"].cpu().numpy()
+    for b in range(2):
+        ref = twist_loop.run_trial(ocfg, 3 + b)
+        k = ref["frames"]
+        assert np.abs(np.diff(ref["q_log"], axis=0)).max() <= 0.05 * 0.05 * (1 + 1e-12)
+        assert rel_err(log[b, :k, :6], ref["q_log"]) <= TOL
+        assert rel_err(log[b, :k, 6:14], ref["f_log"]) <= TOL

@@ -264,7 +264,9 @@ __global__ void __launch_bounds__(128) bd_replay_kernel(const __grid_constant__ 
     }
 }
 
-template <int M, int METHOD>
+// SERVO: the joint servo limits (cfg.v_max / a_max) are a separate instantiation so that the kinematic plant does not
+// carry the six executed-rate registers through the frame loop
+template <int M, int METHOD, bool SERVO>
 __global__ void __launch_bounds__(128, UVS_BD_MINB) bd_closed_loop_kernel(const __grid_constant__ ClosedLoopArgs a) {
     constexpr int GS = GroupSize<M>::value, GPW = 32 / GS, N = 6 * M, LOGW = 6 + 2 * M;
     constexpr int WPC = 4;
@@ -339,6 +341,8 @@ __global__ void __launch_bounds__(128, UVS_BD_MINB) bd_closed_loop_kernel(const 
         HoldState hs;
         double ise = 0.0, iae = 0.0, itae = 0.0;
         double dq[6] = {0, 0, 0, 0, 0, 0};
+        constexpr bool servo = SERVO;
+        double v_prev[6] = {0, 0, 0, 0, 0, 0};      // joint rates executed in the previous frame (SERVO only)
         int status = UVS_STATUS_SUCCESS, frames = 0, flags_all = 0;
         bool alive = trial_ok;
         const double desired = cfg.desired_f[row];
@@ -404,7 +408,12 @@ __global__ void __launch_bounds__(128, UVS_BD_MINB) bd_closed_loop_kernel(const 
                 }
                 ++frames;
 #pragma unroll
-                for (int r = 0; r < 6; ++r) { dq[r] = dq_new[r]; q[r] += dq[r] * cfg.dt; }
+                for (int r = 0; r < 6; ++r) {
+                    dq[r] = dq_new[r];
+                    double v = dq[r];
+                    if (servo) { v = servo_rate(cfg, dq[r], v_prev[r]); v_prev[r] = v; }
+                    q[r] += v * cfg.dt;
+                }
             }
         }
         const double s0 = sqrt(group_sum<GS>(own ? ise * ise : 0.0));
@@ -448,7 +457,8 @@ static cudaError_t bd_closed_launch(const ClosedLoopArgs& a, int sms, cudaStream
     const long long warps = (a.B + GPW - 1) / GPW;
     long long grid = (warps + 3) / 4;
     if (grid > (long long)sms * 8) grid = (long long)sms * 8;
-    bd_closed_loop_kernel<M, METHOD><<<(int)grid, 128, 0, st>>>(a);
+    if ((a.cfg.v_max > 0.0) || (a.cfg.a_max > 0.0)) bd_closed_loop_kernel<M, METHOD, true><<<(int)grid, 128, 0, st>>>(a);
+    else bd_closed_loop_kernel<M, METHOD, false><<<(int)grid, 128, 0, st>>>(a);
     return cudaGetLastError();
 }
 

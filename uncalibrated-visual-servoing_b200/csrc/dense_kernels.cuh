@@ -182,6 +182,8 @@ __global__ void UVS_DENSE_BOUNDS dense_closed_loop_kernel(const __grid_constant_
         int status = UVS_STATUS_SUCCESS, frames = 0, flags_all = 0;
         const double desired = (lane < M) ? cfg.desired_f[lane] : 0.0;
         const double* target = cfg.targets + 3 * ((lane < M ? lane : 0) >> 1);
+        const bool servo = (cfg.v_max > 0.0) || (cfg.a_max > 0.0);
+        double v_prev = 0.0;               // lane j < 6: joint rate executed in the previous frame (servo limits only)
 
         constexpr int FB = 32 / M;         // frames of noise drawn at once: lane = slot * M + coordinate
         const bool philox = (a.io.noise_in == nullptr) && (cfg.noise.type != UVS_NOISE_NONE);
@@ -278,7 +280,9 @@ __global__ void UVS_DENSE_BOUNDS dense_closed_loop_kernel(const __grid_constant_
             ++frames;
             if (lane < 6) {                                              // experiment.py:320,335
                 w.dq[lane] = dq_l;
-                w.q[lane] = q_l + dq_l * cfg.dt;
+                double v = dq_l;
+                if (servo) { v = servo_rate(cfg, dq_l, v_prev); v_prev = v; }
+                w.q[lane] = q_l + v * cfg.dt;
             }
             __syncwarp();
         }

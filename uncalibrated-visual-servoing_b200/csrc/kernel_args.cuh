@@ -69,6 +69,17 @@ UVS_DEV double next_noise_prefetched(HoldState& hs, int hold_cnt, double fresh, 
     return hs.cur;
 }
 
+// joint velocity actually executed for the commanded rate dq (uvs_closed_loop_cfg.v_max / a_max; 0 = unlimited)
+UVS_DEV double servo_rate(const uvs_closed_loop_cfg& cfg, double dq, double v_prev) {
+    double v = dq;
+    if (cfg.a_max > 0.0) {
+        const double dv = cfg.a_max * cfg.dt;
+        v = fmin(fmax(v, v_prev - dv), v_prev + dv);
+    }
+    if (cfg.v_max > 0.0) v = fmin(fmax(v, -cfg.v_max), cfg.v_max);
+    return v;
+}
+
 UVS_DEV void start_pose(const uvs_closed_loop_cfg& cfg, uint64_t trial, double (&q)[6]) {
 #pragma unroll
     for (int j = 0; j < 6; ++j) q[j] = cfg.q_start[j];

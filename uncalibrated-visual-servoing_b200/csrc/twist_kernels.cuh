@@ -149,6 +149,8 @@ __global__ void __launch_bounds__(kTwistThreads, 2) twist_closed_loop_kernel(con
         int status = UVS_STATUS_SUCCESS, frames = 0, flags_all = 0;
         const bool philox = (a.io.noise_in == nullptr) && (cfg.noise.type != UVS_NOISE_NONE);
         double err2 = (double)M;                                           // error = ones(m)  (kalman_4_features.py:70)
+        const bool servo = (cfg.v_max > 0.0) || (cfg.a_max > 0.0);
+        double v_prev[6] = {0, 0, 0, 0, 0, 0};
 
         for (int k = 0; k < T; ++k) {
             if (tw.err_threshold >= 0.0 && !(sqrt(err2) > tw.err_threshold)) break;     // kalman_4_features.py:111
@@ -268,7 +270,9 @@ __global__ void __launch_bounds__(kTwistThreads, 2) twist_closed_loop_kernel(con
 #pragma unroll
             for (int r = 0; r < 6; ++r) {
                 if (lane == r) w.dq[r] = dp[r];
-                q[r] += dq[r] * cfg.dt;                                    // kalman_4_features.py:173,192
+                double v = dq[r];
+                if (servo) { v = servo_rate(cfg, dq[r], v_prev[r]); v_prev[r] = v; }
+                q[r] += v * cfg.dt;                                        // kalman_4_features.py:173,192
             }
             __syncwarp();
         }
