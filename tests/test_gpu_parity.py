@@ -514,3 +514,23 @@ def test_servo_limits_match_oracle(uvs, limits):
                             desired_f=ocfg["desired_f"], v_max=-1.0)
     with pytest.raises(L.UvsError):
         E.closed_loop(bad, 0, 1)
+
+
+def test_long_trials_without_bandwidth_table(uvs):
+    """T > 1024 frames: the closed-loop kernel computes the annealed bandwidth per frame instead of reading its per-CTA
+    table (csrc/dense_kernels.cuh: kSigmaTableMax); same trajectory as the oracle."""
+    from oracle import closed_loop as CL, noise_model as NM
+    L, E = uvs._lib, uvs.engine
+    T = 1100
+    ocfg = CL.make_cfg(method=METHODS["GMCKF"], annealing=True, t_max=T * 0.05, noise_type=NM.WHITE_NOISE,
+                       noise_params=dict(std=1.0), noise_seed=9, pose_seed=3)
+    ref = CL.run_trial(ocfg, 11)
+    for mode in (L.MODE_DENSE, L.MODE_BLOCKDIAG):
+        p = E.filter_params(METHODS["GMCKF"], 4, mode=mode, annealing=True)
+        cfg = E.closed_loop_cfg(p, E.noise_params(NM.WHITE_NOISE, seed=9, std=1.0), T=T, dt=0.05, ibvs_gain=0.2,
+                                q_start=ocfg["q_start"], desired_f=ocfg["desired_f"], pose_seed=3)
+        out = E.closed_loop(cfg, 11, 2, want_log=True)
+        log = out["log"].cpu().numpy()
+        assert int(out["frames"][0]) == ref["frames"] == T
+        assert rel_err(log[0, :, 0:6], ref["q_log"]) <= 1e-6
+        assert rel_err(out["stats"].cpu().numpy()[0], ref["stats"]) <= 1e-6
