@@ -365,6 +365,8 @@ def run_ours(a):
     if logging:
         line["logging"] = logging
     if twist:
+        # KF update with dense X, P, K costs the same F_alg; the twist law adds two 6-column pseudo-inverses
+        twist["roofline_frac_by_F_alg"] = twist["value"] * F_ALG / 1e12 / peak_tf
         line["twist"] = twist
     if not a.no_cpu_baseline and world == 1:
         v, cores, frames, wall = cpu_sample(CPU_TRIALS_PER_CORE)

@@ -18,3 +18,5 @@ timeout 900 ncu --set full --clock-control none -k regex:dense_closed_loop -c 1 
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:bd_closed_loop -c 1 -o $O/bd_full -f \
     python bench.py --steps 1 --warmup 1 --mode blockdiag --no-cpu-baseline --no-blockdiag-extra --no-extras > $O/ncu_bd.log 2>&1
 ls -la $O
+timeout 900 ncu --set full --clock-control none -k regex:twist_closed_loop -c 1 -o $O/twist_full -f \
+    python bench.py --steps 1 --warmup 1 --trials 14800 --no-cpu-baseline --no-blockdiag-extra > $O/ncu_twist.log 2>&1

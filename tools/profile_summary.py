@@ -48,7 +48,8 @@ def main():
           "Raw reports stay in gpurun_out/ (scratch).  Per-launch times under ncu are serialised and cold-cache: "
           "compare shares, not absolutes; the bench line's own CUDA-event timing is in the *_bench.json beside this file.", ""]
     traffic = {}
-    for rep, steps_note in (("dense_full", "dense"), ("bd_full", "blockdiag"), ("dense_full_100k", "dense, bench-sized launch")):
+    for rep, steps_note in (("dense_full", "dense"), ("bd_full", "blockdiag"), ("dense_full_100k", "dense, bench-sized launch"),
+                            ("twist_full", "camera-twist pipeline, 20 k trials x 440 frames")):
         path = os.path.join(src, rep + ".ncu-rep")
         if not os.path.exists(path):
             continue
@@ -66,7 +67,7 @@ def main():
                     md.append(f"| {h} | {v[i]} | cycles per issued instruction |")
             md.append("")
             ir, iw = hdr.index("dram__bytes_read.sum"), hdr.index("dram__bytes_write.sum")
-            if rep != "dense_full":            # bench-sized launches only
+            if rep not in ("dense_full", "twist_full"):            # bench-sized launches only
                 key = ("dense" if "dense" in name else "bd") + "_closed_loop_kernel<8, GMCKF>"
                 key = key.replace("bd_", "blockdiag_")
                 traffic[key] = to_bytes(v[ir], units[ir]) + to_bytes(v[iw], units[iw])

@@ -72,7 +72,9 @@ UVS_DEV void ur10_chain_columns(const double (&s)[6], const double (&c)[6], int 
     T6 = T;
 }
 
-template <int M, int METHOD>
+// FAST: Q = R = NULL and the Joseph form known at compile time (as in dense_closed_loop_kernel); with M >= 6 the covariance
+// update then runs inside the first pseudo-inverse (ibvs_with_rank_update).
+template <int M, int METHOD, bool FAST>
 __global__ void __launch_bounds__(kTwistThreads, 2) twist_closed_loop_kernel(const __grid_constant__ TwistArgs a) {
     constexpr int N = 6 * M;
     constexpr bool ANALYTIC = METHOD == UVS_METHOD_ANALYTICAL;
@@ -204,6 +206,8 @@ __global__ void __launch_bounds__(kTwistThreads, 2) twist_closed_loop_kernel(con
 
             // ---- Jacobian: estimated (filter regressed on dp) or calibrated ----
             double kappa = 1.0;
+            constexpr bool DEFER = FAST && M >= 6 && !MCKF && !ANALYTIC;
+            bool rank_pending = false;
             if constexpr (ANALYTIC) {
                 const double f_p = shfl_d(f_l, lane ^ 1);
                 if (lane < M) {
@@ -218,15 +222,21 @@ __global__ void __launch_bounds__(kTwistThreads, 2) twist_closed_loop_kernel(con
                 load6(w.dq, h);                                            // kalman_4_features.py:152-156
                 const double sigma = annealed_bw(cfg.filt.kernel_bw, cfg.filt.annealing, k, T);
                 StepOut so;
-                kappa = dense_step<M, FILTER>(pb, w, cc, cfg.filt, h, z, sigma, lane, so);
+                kappa = dense_step<M, FILTER, DEFER, FAST>(pb, w, cc, cfg.filt, h, z, sigma, lane, so, 1.0 / (sigma * sigma));
                 flags_all |= so.flags;
+                rank_pending = so.rank_pending;
             }
 
             // ---- control: dp = -GAIN pinv(J) e ; dx = kron(I2, R^T) dp ; dq = pinv(J_geom) dx ----
             const double e_l = f_l - desired;
             double x[6];
             int ib_flags = 0;
-            pinv_warp<M>(w.X, kappa * e_l, w.ib, lane, x, ib_flags);
+            if constexpr (DEFER) {
+                if (rank_pending) ibvs_with_rank_update<M>(pb, w.Pd, w.Kt, w.Ut, w.X, kappa * e_l, w.ib, lane, x, ib_flags);
+                else pinv_warp<M>(w.X, kappa * e_l, w.ib, lane, x, ib_flags);
+            } else {
+                pinv_warp<M>(w.X, kappa * e_l, w.ib, lane, x, ib_flags);
+            }
             double dp[6];
 #pragma unroll
             for (int r = 0; r < 6; ++r) dp[r] = ((tw.dp_zero_mask >> r) & 1) ? 0.0 : -cfg.ibvs_gain * x[r];
@@ -315,7 +325,12 @@ static cudaError_t twist_launch(Kernel kernel, const TwistArgs& a, size_t smem, 
 
 #define UVS_DEFINE_TWIST_LAUNCHER(MM)                                                                            \
     template <int METHOD> static cudaError_t twist_one_##MM(const TwistArgs& a, int sms, cudaStream_t st) {     \
-        return twist_launch(twist_closed_loop_kernel<MM, METHOD>, a,                                             \
+        const uvs_filter_params& fp = a.cfg.filt;                                                                \
+        constexpr bool CAN_FAST = METHOD != UVS_METHOD_MCKF && METHOD != UVS_METHOD_ANALYTICAL;                  \
+        if (CAN_FAST && fp.Q == nullptr && fp.R == nullptr && fp.joseph)                                         \
+            return twist_launch(twist_closed_loop_kernel<MM, METHOD, CAN_FAST>, a,                               \
+                                twist_smem_bytes<MM, METHOD == UVS_METHOD_MCKF>(kTwistWarps), sms, st);          \
+        return twist_launch(twist_closed_loop_kernel<MM, METHOD, false>, a,                                      \
                             twist_smem_bytes<MM, METHOD == UVS_METHOD_MCKF>(kTwistWarps), sms, st);              \
     }                                                                                                            \
     template <> cudaError_t launch_twist_loop<MM>(const TwistArgs& a, int sms, cudaStream_t st) {                \
