@@ -117,10 +117,13 @@ typedef struct uvs_closed_loop_cfg {
     const double* P0;        /* device [N,N] or NULL = identity (experiment.py:73)         */
     /* joint servo limits of the scenes (position-controlled joints, Ruc v_max = 1.0472 rad/s,
      * a_max = 6.283 rad/s^2); 0 = unlimited = the kinematic plant q <- q + dq dt of experiment.py:320,335.
-     * Per frame: v = clamp(dq, v_prev -+ a_max dt) ; v = clamp(v, -+v_max) ; q += v dt ; v_prev = v.
+     * servo_gain: fraction of the commanded step a position-controlled joint covers within one frame (first-order
+     * servo lag; the scenes' joints run a P controller, gain 0.1, at a 5 ms dynamics step); 0 or 1 = exact tracking.
+     * Per frame: v = servo_gain dq ; v = clamp(v, v_prev -+ a_max dt) ; v = clamp(v, -+v_max) ; q += v dt ; v_prev = v.
      * The filter regressor stays the COMMANDED dq, as in the reference (experiment.py:188). */
     double v_max;
     double a_max;
+    double servo_gain;
 } uvs_closed_loop_cfg;
 
 /* buffers of a closed-loop batch; any optional pointer may be NULL */

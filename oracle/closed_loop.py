@@ -23,7 +23,7 @@ DEFAULTS = dict(
     noise_params=dict(alpha=1.5, beta=0.0, gamma=1.0, delta=0.0),
     hold_cnt=0, noise_seed=123456, pose_seed=12345, change_q_start=True,
     fov_check=False, P0=None, Q=None, R=None, targets=None, structured=False,
-    v_max=0.0, a_max=0.0,        # joint servo limits (SURVEY.md Appendix A 'Joints'); 0 = kinematic plant
+    v_max=0.0, a_max=0.0, servo_gain=0.0,        # joint servo model (SURVEY.md Appendix A 'Joints'); 0 = kinematic plant
 )
 
 
@@ -37,6 +37,8 @@ def servo_rate(cfg, dq, v_prev):
     """Joint rates actually executed for the commanded dq under the scene's servo limits
     (include/uvs_b200.h: uvs_closed_loop_cfg.v_max / a_max): acceleration clamp, then velocity clamp."""
     v = np.array(dq, dtype=float)
+    if cfg.get("servo_gain", 0.0) > 0.0:
+        v = cfg["servo_gain"] * v
     if cfg.get("a_max", 0.0) > 0.0:
         dv = cfg["a_max"] * cfg["dt"]
         v = np.minimum(np.maximum(v, v_prev - dv), v_prev + dv)

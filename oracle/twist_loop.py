@@ -36,7 +36,7 @@ DEFAULTS = dict(
     kernel_bw=20.0, fpi_threshold=0.01, fpi_epoch_max=100, annealing=False, joseph=True, mckf_skip=False,
     noise_type=0, noise_params={}, hold_cnt=0,
     noise_seed=123456, pose_seed=12345, change_q_start=False, targets=None, P0=None, Q=None, R=None,
-    v_max=0.0, a_max=0.0,
+    v_max=0.0, a_max=0.0, servo_gain=0.0,
 )
 
 

@@ -36,14 +36,14 @@ def test_struct_layout_matches_c(lib, tmp_path):
                    'int main(){printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu %zu\\n", sizeof(uvs_filter_params), sizeof(uvs_noise_params),'
                    'sizeof(uvs_closed_loop_cfg), sizeof(uvs_closed_loop_io), offsetof(uvs_closed_loop_cfg, sweep),'
                    'offsetof(uvs_closed_loop_cfg, P0), offsetof(uvs_closed_loop_io, p_layout), sizeof(uvs_twist_cfg),'
-                   'offsetof(uvs_twist_cfg, err_threshold), offsetof(uvs_closed_loop_cfg, a_max));return 0;}\n')
+                   'offsetof(uvs_twist_cfg, err_threshold), offsetof(uvs_closed_loop_cfg, servo_gain));return 0;}\n')
     exe = tmp_path / "sz"
     subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)])
     got = [int(v) for v in subprocess.check_output([str(exe)]).split()]
     want = [C.sizeof(lib.FilterParams), C.sizeof(lib.NoiseParams), C.sizeof(lib.ClosedLoopCfg),
             C.sizeof(lib.ClosedLoopIO), lib.ClosedLoopCfg.sweep.offset, lib.ClosedLoopCfg.P0.offset,
             lib.ClosedLoopIO.p_layout.offset, C.sizeof(lib.TwistCfg), lib.TwistCfg.err_threshold.offset,
-            lib.ClosedLoopCfg.a_max.offset]
+            lib.ClosedLoopCfg.servo_gain.offset]
     assert got == want
 
 

@@ -479,8 +479,8 @@ def test_experiment_api_drop_in(uvs):
                        method_params=dict(initial_guess=True))
 
 
-@pytest.mark.parametrize("limits", [dict(v_max=0.2), dict(a_max=6.283), dict(v_max=0.3, a_max=2.0)],
-                         ids=["vmax", "amax", "both"])
+@pytest.mark.parametrize("limits", [dict(v_max=0.2), dict(a_max=6.283), dict(v_max=0.3, a_max=2.0), dict(servo_gain=0.65)],
+                         ids=["vmax", "amax", "both", "lag"])
 def test_servo_limits_match_oracle(uvs, limits):
     """SURVEY §8f row 3 (first step): the scenes' joint servo limits (Appendix A: 60 deg/s, 360 deg/s^2) as an
     acceleration + velocity clamp on the executed joint rate, both kernel families against the oracle."""

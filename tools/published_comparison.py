@@ -6,7 +6,8 @@
 The only quantities the reference publishes are the ITAE mean +- std per noise level of results/results{1,2,3}.fig
 (decoded from the .fig files; CoppeliaSim in the loop, 100 experiments per level).  This script runs
 the same sweep — alpha-stable noise, alpha = linspace(1, 2, 12), 4 features, T = 300, ibvs_gain = 0.2 (config.json) —
-for every published series on the kinematic plant (and again with the scenes' joint servo limits), `epoch` trials per
+for every published series on the kinematic plant (and again with the scenes' first-order servo lag, and with their
+rate limits), `epoch` trials per
 level, and writes both tables side by side.  The published tables are parsed from BASELINE.md at run time.
 
 What to expect: order-of-magnitude agreement — the plants differ (kinematic UR10 + point features here,
@@ -81,7 +82,10 @@ def main():
     a = ap.parse_args()
     import uvs_b200 as uvs
     pub = published_tables(os.path.join(ROOT, "BASELINE.md"))
-    plants = {"kinematic": {}, "servo limits (60 deg/s, 360 deg/s^2)": dict(v_max=1.0472, a_max=6.283)}
+    # servo lag: the scenes' joints are position-controlled with P-gain 0.1 at a 5 ms dynamics step, i.e.
+    # a joint covers 1 - 0.9^10 = 0.651 of the commanded step within one 50 ms frame
+    plants = {"kinematic": {}, "first-order servo lag (servo_gain = 1 - 0.9^10 = 0.651)": dict(servo_gain=1.0 - 0.9 ** 10),
+              "servo limits (60 deg/s, 360 deg/s^2)": dict(v_max=1.0472, a_max=6.283)}
     md = ["# Closed-loop ITAE: this engine vs the reference's published curves", "",
           f"`python tools/published_comparison.py --epoch {a.epoch}` on one B200.  Published = mean ± std of 100 CoppeliaSim "
           "experiments per level, decoded from `results/results{1,2,3}.fig` (BASELINE.md §1).  Ours = mean ± std "

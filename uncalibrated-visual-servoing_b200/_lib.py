@@ -45,7 +45,7 @@ class ClosedLoopCfg(C.Structure):
                 ("sweep_epoch", C.c_int32), ("sweep_param", C.c_int32), ("reserved", C.c_int32),
                 ("dt", C.c_double), ("ibvs_gain", C.c_double), ("q_start", C.c_double * 6),
                 ("desired_f", C.c_double * 8), ("targets", C.c_double * 12), ("pose_seed", C.c_uint64),
-                ("sweep", C.c_double * UVS_MAX_SWEEP), ("P0", _dp), ("v_max", C.c_double), ("a_max", C.c_double)]
+                ("sweep", C.c_double * UVS_MAX_SWEEP), ("P0", _dp), ("v_max", C.c_double), ("a_max", C.c_double), ("servo_gain", C.c_double)]
 
 
 class ClosedLoopIO(C.Structure):

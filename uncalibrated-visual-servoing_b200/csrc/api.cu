@@ -199,7 +199,8 @@ int uvs_closed_loop(const uvs_closed_loop_cfg* cfg, uint64_t trial0, int64_t B,
     if (!valid_method(fp.method)) return set_error(UVS_ERR_INVALID, "method %d is not a filter method", fp.method);
     if (cfg->T < 1 || B < 0) return set_error(UVS_ERR_INVALID, "T=%d B=%lld", cfg->T, (long long)B);
     if (cfg->sweep_len < 0 || cfg->sweep_len > UVS_MAX_SWEEP) return set_error(UVS_ERR_INVALID, "sweep_len");
-    if (!(cfg->v_max >= 0.0) || !(cfg->a_max >= 0.0)) return set_error(UVS_ERR_INVALID, "v_max / a_max must be >= 0");
+    if (!(cfg->v_max >= 0.0) || !(cfg->a_max >= 0.0) || !(cfg->servo_gain >= 0.0))
+        return set_error(UVS_ERR_INVALID, "v_max / a_max / servo_gain must be >= 0");
     if (!fp.joseph && fp.method == UVS_METHOD_MCKF)
         return set_error(UVS_ERR_UNSUPPORTED, "MCKF requires the Joseph update");
     if (int rc = check_noise(cfg->noise)) return rc;
@@ -230,7 +231,8 @@ int uvs_twist_loop(const uvs_closed_loop_cfg* cfg, const uvs_twist_cfg* tw, uint
     if (fp.method != UVS_METHOD_ANALYTICAL && !valid_method(fp.method)) return set_error(UVS_ERR_INVALID, "method %d", fp.method);
     if (cfg->T < 1 || B < 0) return set_error(UVS_ERR_INVALID, "T=%d B=%lld", cfg->T, (long long)B);
     if (cfg->sweep_len < 0 || cfg->sweep_len > UVS_MAX_SWEEP) return set_error(UVS_ERR_INVALID, "sweep_len");
-    if (!(cfg->v_max >= 0.0) || !(cfg->a_max >= 0.0)) return set_error(UVS_ERR_INVALID, "v_max / a_max must be >= 0");
+    if (!(cfg->v_max >= 0.0) || !(cfg->a_max >= 0.0) || !(cfg->servo_gain >= 0.0))
+        return set_error(UVS_ERR_INVALID, "v_max / a_max / servo_gain must be >= 0");
     if (tw->x0_mode < UVS_X0_ZEROS || tw->x0_mode > UVS_X0_RANDOM) return set_error(UVS_ERR_INVALID, "x0_mode %d", tw->x0_mode);
     if (tw->depth_mode != UVS_DEPTH_DISTANCE && tw->depth_mode != UVS_DEPTH_HEIGHT) return set_error(UVS_ERR_INVALID, "depth_mode %d", tw->depth_mode);
     if (tw->dp_zero_mask < 0 || tw->dp_zero_mask > 63) return set_error(UVS_ERR_INVALID, "dp_zero_mask %d", tw->dp_zero_mask);

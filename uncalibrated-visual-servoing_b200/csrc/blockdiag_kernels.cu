@@ -457,7 +457,7 @@ static cudaError_t bd_closed_launch(const ClosedLoopArgs& a, int sms, cudaStream
     const long long warps = (a.B + GPW - 1) / GPW;
     long long grid = (warps + 3) / 4;
     if (grid > (long long)sms * 8) grid = (long long)sms * 8;
-    if ((a.cfg.v_max > 0.0) || (a.cfg.a_max > 0.0)) bd_closed_loop_kernel<M, METHOD, true><<<(int)grid, 128, 0, st>>>(a);
+    if ((a.cfg.v_max > 0.0) || (a.cfg.a_max > 0.0) || (a.cfg.servo_gain > 0.0 && a.cfg.servo_gain != 1.0)) bd_closed_loop_kernel<M, METHOD, true><<<(int)grid, 128, 0, st>>>(a);
     else bd_closed_loop_kernel<M, METHOD, false><<<(int)grid, 128, 0, st>>>(a);
     return cudaGetLastError();
 }

@@ -182,7 +182,7 @@ __global__ void UVS_DENSE_BOUNDS dense_closed_loop_kernel(const __grid_constant_
         int status = UVS_STATUS_SUCCESS, frames = 0, flags_all = 0;
         const double desired = (lane < M) ? cfg.desired_f[lane] : 0.0;
         const double* target = cfg.targets + 3 * ((lane < M ? lane : 0) >> 1);
-        const bool servo = (cfg.v_max > 0.0) || (cfg.a_max > 0.0);
+        const bool servo = (cfg.v_max > 0.0) || (cfg.a_max > 0.0) || (cfg.servo_gain > 0.0 && cfg.servo_gain != 1.0);
         double v_prev = 0.0;               // lane j < 6: joint rate executed in the previous frame (servo limits only)
 
         constexpr int FB = 32 / M;         // frames of noise drawn at once: lane = slot * M + coordinate

@@ -71,7 +71,7 @@ UVS_DEV double next_noise_prefetched(HoldState& hs, int hold_cnt, double fresh, 
 
 // joint velocity actually executed for the commanded rate dq (uvs_closed_loop_cfg.v_max / a_max; 0 = unlimited)
 UVS_DEV double servo_rate(const uvs_closed_loop_cfg& cfg, double dq, double v_prev) {
-    double v = dq;
+    double v = (cfg.servo_gain > 0.0) ? cfg.servo_gain * dq : dq;
     if (cfg.a_max > 0.0) {
         const double dv = cfg.a_max * cfg.dt;
         v = fmin(fmax(v, v_prev - dv), v_prev + dv);

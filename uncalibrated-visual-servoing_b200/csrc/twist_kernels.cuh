@@ -151,7 +151,7 @@ __global__ void __launch_bounds__(kTwistThreads, 2) twist_closed_loop_kernel(con
         int status = UVS_STATUS_SUCCESS, frames = 0, flags_all = 0;
         const bool philox = (a.io.noise_in == nullptr) && (cfg.noise.type != UVS_NOISE_NONE);
         double err2 = (double)M;                                           // error = ones(m)  (kalman_4_features.py:70)
-        const bool servo = (cfg.v_max > 0.0) || (cfg.a_max > 0.0);
+        const bool servo = (cfg.v_max > 0.0) || (cfg.a_max > 0.0) || (cfg.servo_gain > 0.0 && cfg.servo_gain != 1.0);
         double v_prev[6] = {0, 0, 0, 0, 0, 0};
 
         for (int k = 0; k < T; ++k) {

@@ -167,7 +167,7 @@ def start_poses(q_start, pose_seed, change_q_start, trial0, B, device="cuda"):
 
 def closed_loop_cfg(filt, noise, *, T, dt, ibvs_gain, q_start, desired_f, targets=None, initial_guess=True,
                     change_q_start=True, fov_check=False, pose_seed=12345, sweep=None, sweep_epoch=1,
-                    sweep_param=0, P0=None, v_max=0.0, a_max=0.0):
+                    sweep_param=0, P0=None, v_max=0.0, a_max=0.0, servo_gain=0.0):
     cfg = L.ClosedLoopCfg()
     cfg.filt = filt
     cfg.noise = noise
@@ -191,7 +191,7 @@ def closed_loop_cfg(filt, noise, *, T, dt, ibvs_gain, q_start, desired_f, target
     cfg.pose_seed = int(pose_seed) & 0xFFFFFFFFFFFFFFFF
     cfg._keep = (filt, dev(P0))
     cfg.P0 = _ptr(cfg._keep[1]).value
-    cfg.v_max, cfg.a_max = float(v_max), float(a_max)        # joint servo limits (0 = the kinematic plant)
+    cfg.v_max, cfg.a_max, cfg.servo_gain = float(v_max), float(a_max), float(servo_gain)   # servo model (0 = kinematic plant)
     return cfg
 
 
