@@ -155,6 +155,18 @@ def test_load_config_follows_main_py():
             sweep.load_config(_config(**bad))
 
 
+def test_load_config_optional_plant_block():
+    """Additive: "plant": {servo_gain, v_max, a_max} reaches the estimator kwargs; a config without it is the kinematic plant."""
+    cfg = _config()
+    assert not {"servo_gain", "v_max", "a_max"} & set(sweep.load_config(cfg)["method_params"])
+    cfg["plant"] = {"servo_gain": 0.651, "v_max": 1.0472}
+    mp_ = sweep.load_config(cfg)["method_params"]
+    assert mp_["servo_gain"] == 0.651 and mp_["v_max"] == 1.0472 and "a_max" not in mp_
+    cfg["plant"] = {"friction": 1.0}
+    with pytest.raises(SystemExit):
+        sweep.load_config(cfg)
+
+
 def test_run_sweep_fails_loudly_without_gpu():
     if torch.cuda.is_available():
         pytest.skip("CUDA present")
