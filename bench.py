@@ -355,11 +355,16 @@ def run_ours(a):
                      "traffic_unit": "bytes per launch (ncu dram read + write); algorithmic: 32 B per trial of results",
                      "kernel": f"{a.mode}_closed_loop_kernel<8, GMCKF>", "kernel_ms": main["kernel_ms"],
                      "flops_per_filter_step_algorithmic": F_ALG,
+                     "flops_per_filter_step_executed": ncu_traffic("dense_executed_flops_per_filter_step") if a.mode == "dense" else None,
                      "peak_source": "measured in this run: uvs_fp64_peak (register-resident DFMA chains on every SM); "
                                     "MEASURED_PEAKS.json has no FP64 entry; datasheet 148 SM x 64 lanes x 2 x 1.965 GHz = 37.2"},
         "failed_trials": float(main["n_fail"].sum()),
         "itae_mean_per_level": [float(s[2, 1] / max(s[2, 0], 1.0)) for s in main["sums"]],
     }
+    ex_fl = line["roofline"]["flops_per_filter_step_executed"]
+    if ex_fl:       # hardware-counted (committed ncu capture): executed flops are ~0.6 F_alg because only the lower blocks are updated
+        line["roofline"]["achieved_executed"] = steps_per_launch * ex_fl / (main["kernel_ms"] * 1e-3) / 1e12
+        line["roofline"]["frac_executed"] = line["roofline"]["achieved_executed"] / peak_tf
     if extra:
         line["blockdiag"] = extra
     if logging:

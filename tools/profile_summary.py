@@ -66,6 +66,19 @@ def main():
                 if "issue_stalled" in h and h.endswith("per_issue_active.ratio") and float(v[i] or 0) > 0.05:
                     md.append(f"| {h} | {v[i]} | cycles per issued instruction |")
             md.append("")
+            if rep == "dense_full":
+                # hardware-counted FP64 flops per filter-step of the 14 800-trial x 300-frame capture (must sit
+                # within [0.5, 1.1] x F_alg): 2 dfma + dmul + dadd thread instructions, per elapsed cycle x elapsed cycles
+                try:
+                    per_cycle = sum(k * float(v[hdr.index(f"smsp__sass_thread_inst_executed_op_{op}_pred_on.sum.per_cycle_elapsed")])
+                                    for op, k in (("dfma", 2.0), ("dmul", 1.0), ("dadd", 1.0)))
+                    cycles = float(v[hdr.index("smsp__cycles_elapsed.max")]) if "smsp__cycles_elapsed.max" in hdr \
+                        else float(v[hdr.index("sm__cycles_elapsed.max")])
+                    traffic["dense_executed_flops_per_filter_step"] = per_cycle * cycles / (14800 * 300)
+                    md.insert(len(md) - 1, f"| executed FP64 flops per filter-step (2 dfma + dmul + dadd) | "
+                                           f"{traffic['dense_executed_flops_per_filter_step']:.0f} | flop |")
+                except (ValueError, KeyError):
+                    pass
             ir, iw = hdr.index("dram__bytes_read.sum"), hdr.index("dram__bytes_write.sum")
             if rep not in ("dense_full", "twist_full"):            # bench-sized launches only
                 key = ("dense" if "dense" in name else "bd") + "_closed_loop_kernel<8, GMCKF>"
