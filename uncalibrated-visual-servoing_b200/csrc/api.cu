@@ -268,18 +268,20 @@ int uvs_closed_loop_host(const uvs_closed_loop_cfg* cfg, uint64_t trial0, int64_
     // and the call ends with one stream synchronisation
     const size_t n_stats = sizeof(double) * 3 * (size_t)B, n_i32 = sizeof(int32_t) * (size_t)B;
     cudaStream_t st = cudaStreamPerThread;
-    struct Scratch { unsigned char* p = nullptr; size_t cap = 0; int dev = -1; };
-    static thread_local Scratch sc;
+    struct Scratch { unsigned char* p = nullptr; size_t cap = 0; };
+    constexpr int kMaxDevices = 64;
+    static thread_local Scratch per_device[kMaxDevices];       // one block per (host thread, device)
     int dev = 0;
     int rc = check_cuda(cudaGetDevice(&dev), "cudaGetDevice");
     if (rc) return rc;
-    if (sc.dev != dev || sc.cap < n_stats + 2 * n_i32) {
-        if (sc.p && sc.dev == dev) cudaFree(sc.p);
+    if (dev < 0 || dev >= kMaxDevices) return set_error(UVS_ERR_UNSUPPORTED, "device ordinal %d", dev);
+    Scratch& sc = per_device[dev];
+    if (sc.cap < n_stats + 2 * n_i32) {
+        if (sc.p) cudaFree(sc.p);
         sc = Scratch{};
         rc = check_cuda(cudaMalloc((void**)&sc.p, n_stats + 2 * n_i32), "cudaMalloc result scratch");
         if (rc) { sc = Scratch{}; return rc; }
         sc.cap = n_stats + 2 * n_i32;
-        sc.dev = dev;
     }
     unsigned char* scratch = sc.p;
     double* d_stats = reinterpret_cast<double*>(scratch);
