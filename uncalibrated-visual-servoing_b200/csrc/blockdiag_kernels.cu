@@ -16,11 +16,12 @@
 //   P = P^- - K v^T - v K^T + (s0 + 1) K K^T            (Joseph, experiment.py:297)
 //   P = P^- - K v^T                                      (joseph = 0, tests/kalman_1_feature.py:126)
 #include "blockdiag_kernels.h"
+#include <cstdlib>
 #include "smallmat.cuh"
 
 // resident CTAs per SM asked of ptxas for the closed-loop kernel (register cap 65536 / (MINB * 128))
 #ifndef UVS_BD_MINB
-#define UVS_BD_MINB 2
+#define UVS_BD_MINB 3
 #endif
 
 namespace uvs {
@@ -441,12 +442,28 @@ __global__ void __launch_bounds__(128, UVS_BD_MINB) bd_closed_loop_kernel(const 
     }
 }
 
+// grid = whole waves of resident CTAs (occupancy API), so that the statically strided trial loop ends evenly on every SM
+#ifndef UVS_BD_WAVES
+#define UVS_BD_WAVES 16
+#endif
+template <typename Kernel>
+static long long bd_grid(Kernel kernel, long long need, int sms) {
+    int per_sm = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, 128, 0) != cudaSuccess || per_sm < 1) per_sm = 2;
+    int waves = UVS_BD_WAVES;
+    if (const char* e = getenv("UVS_BD_WAVES")) {          // tuning experiments only
+        const int v = atoi(e);
+        if (v >= 1) waves = v;
+    }
+    const long long grid = (long long)sms * per_sm * waves;
+    return need < grid ? need : grid;
+}
+
 template <int M, int METHOD>
 static cudaError_t bd_replay_launch(const ReplayArgs& a, int sms, cudaStream_t st) {
     constexpr int GPW = 32 / GroupSize<M>::value;
     const long long warps = (a.B + GPW - 1) / GPW;
-    long long grid = (warps + 3) / 4;
-    if (grid > (long long)sms * 8) grid = (long long)sms * 8;
+    const long long grid = bd_grid(bd_replay_kernel<M, METHOD>, (warps + 3) / 4, sms);
     bd_replay_kernel<M, METHOD><<<(int)grid, 128, 0, st>>>(a);
     return cudaGetLastError();
 }
@@ -455,10 +472,11 @@ template <int M, int METHOD>
 static cudaError_t bd_closed_launch(const ClosedLoopArgs& a, int sms, cudaStream_t st) {
     constexpr int GPW = 32 / GroupSize<M>::value;
     const long long warps = (a.B + GPW - 1) / GPW;
-    long long grid = (warps + 3) / 4;
-    if (grid > (long long)sms * 8) grid = (long long)sms * 8;
-    if ((a.cfg.v_max > 0.0) || (a.cfg.a_max > 0.0) || (a.cfg.servo_gain > 0.0 && a.cfg.servo_gain != 1.0)) bd_closed_loop_kernel<M, METHOD, true><<<(int)grid, 128, 0, st>>>(a);
-    else bd_closed_loop_kernel<M, METHOD, false><<<(int)grid, 128, 0, st>>>(a);
+    const long long need = (warps + 3) / 4;
+    if ((a.cfg.v_max > 0.0) || (a.cfg.a_max > 0.0) || (a.cfg.servo_gain > 0.0 && a.cfg.servo_gain != 1.0))
+        bd_closed_loop_kernel<M, METHOD, true><<<(int)bd_grid(bd_closed_loop_kernel<M, METHOD, true>, need, sms), 128, 0, st>>>(a);
+    else
+        bd_closed_loop_kernel<M, METHOD, false><<<(int)bd_grid(bd_closed_loop_kernel<M, METHOD, false>, need, sms), 128, 0, st>>>(a);
     return cudaGetLastError();
 }
 
