@@ -250,13 +250,14 @@ template <int M, bool RANK2>
 UVS_DEV void rank_update_diag(double* Pd, const double* Kt, const double* Ut, int lane) {
     constexpr int N = 6 * M, LD = N + 2;
     const int d = lane >> 2, s = lane & 3;
-    if (M == 8 || d < M) {                     // M = 8: all 32 lanes, no branch
-        const int rowA = 5 - s;
-        const int rowB = (s == 2) ? 1 : 0;
-        double* pd = Pd + d * kBlkStride;
+    const bool on = (M == 8) || (d < M);       // M = 8: all 32 lanes, no branch
+    const int rowA = 5 - s;
+    const int rowB = (s == 2) ? 1 : 0;
+    double* pd = Pd + (on ? d : 0) * kBlkStride;
+    double accA[6], accB[2];
+    if (on) {
         const double* kt = Kt + 6 * d;
         const double* ut = Ut + 6 * d;
-        double accA[6], accB[2];
         load6(pd + rowA * 6, accA);
         accB[0] = pd[rowB * 6]; accB[1] = pd[rowB * 6 + 1];
 #pragma unroll
@@ -278,6 +279,12 @@ UVS_DEV void rank_update_diag(double* Pd, const double* Kt, const double* Ut, in
                 accB[1] -= uB * kk[1];
             }
         }
+    }
+    // every lane has read its rows (including the mirrored upper-triangle entries it computes and drops) before any
+    // lane writes them: without this barrier compute-sanitizer's racecheck reports those unused reads against the
+    // mirror writes of the neighbouring lanes
+    __syncwarp();
+    if (on) {
 #pragma unroll
         for (int e = 0; e < 6; ++e)
             if (e <= rowA) { pd[rowA * 6 + e] = accA[e]; pd[e * 6 + rowA] = accA[e]; }
