@@ -74,3 +74,28 @@ def test_host_layer_fails_loudly_without_gpu(lib):
     import uvs_b200
     with pytest.raises(lib.UvsError):
         uvs_b200.engine.fp64_peak()
+
+
+def test_twist_loop_validates_before_touching_the_device(lib):
+    """uvs_twist_loop / uvs_closed_loop reject bad scalar arguments with UVS_ERR_INVALID (no CUDA call is needed to say so)."""
+    handle = lib.load()
+    cfg, tw, io = lib.ClosedLoopCfg(), lib.TwistCfg(), lib.ClosedLoopIO()
+    cfg.filt.method, cfg.filt.nf, cfg.filt.joseph, cfg.T = 2, 4, 1, 10
+    io.stats, io.status = 8, 8                                   # never dereferenced on the error paths below
+    tw.x0_mode, tw.focal_x0, tw.focal = 7, 1.0, 1.0
+    assert handle.uvs_twist_loop(C.byref(cfg), C.byref(tw), 0, 1, C.byref(io), None) == -1
+    assert "x0_mode" in lib.last_error()
+    tw.x0_mode, tw.dp_zero_mask = 1, 64
+    assert handle.uvs_twist_loop(C.byref(cfg), C.byref(tw), 0, 1, C.byref(io), None) == -1
+    tw.dp_zero_mask, tw.focal_x0 = 0, 0.0
+    assert handle.uvs_twist_loop(C.byref(cfg), C.byref(tw), 0, 1, C.byref(io), None) == -1 and "focal" in lib.last_error()
+    tw.focal_x0 = 1024.0
+    cfg.servo_gain = -0.5
+    assert handle.uvs_twist_loop(C.byref(cfg), C.byref(tw), 0, 1, C.byref(io), None) == -1
+    assert handle.uvs_closed_loop(C.byref(cfg), 0, 1, C.byref(io), None) == -1 and "servo_gain" in lib.last_error()
+    cfg.servo_gain = 0.0
+    cfg.filt.mode = 2                                            # the twist loop has no block-diagonal family
+    assert handle.uvs_twist_loop(C.byref(cfg), C.byref(tw), 0, 1, C.byref(io), None) == -3
+    cfg.filt.mode, cfg.filt.method = 0, 1                        # ANALYTICAL is a twist-loop method, not a closed-loop one
+    assert handle.uvs_closed_loop(C.byref(cfg), 0, 1, C.byref(io), None) == -1 and "method" in lib.last_error()
+    assert handle.uvs_twist_loop(C.byref(cfg), C.byref(tw), 0, 0, C.byref(io), None) == 0      # empty batch: no-op
