@@ -534,3 +534,30 @@ def test_long_trials_without_bandwidth_table(uvs):
         assert int(out["frames"][0]) == ref["frames"] == T
         assert rel_err(log[0, :, 0:6], ref["q_log"]) <= 1e-6
         assert rel_err(out["stats"].cpu().numpy()[0], ref["stats"]) <= 1e-6
+
+
+@pytest.mark.parametrize("nf", [3, 4])
+def test_closed_loop_rank_deficient_start_uses_the_fallback(uvs, nf):
+    """A rank-1 initial Jacobian: the first command must be the minimum-norm solution np.linalg.pinv gives (experiment.py:312)
+    — computed by the cooperative Jacobi fallback (dense M = 6, block-diagonal) or the serial one (dense M = 8)."""
+    from oracle import closed_loop as CL, kinematics as K
+    L, E = uvs._lib, uvs.engine
+    m, N = 2 * nf, 12 * nf
+    rng = np.random.default_rng(nf)
+    row = rng.standard_normal(6) * 50.0
+    X0 = (np.outer(rng.uniform(0.5, 2.0, m), row)).reshape(N)           # every row parallel to `row`: rank 1
+    desired = [153.5, 144.5, 125.5, 116.5, 99.5, 144.5] if nf == 3 else CL.DEFAULTS["desired_f"]
+    q0 = np.array(CL.DEFAULTS["q_start"]) + np.array([0.0, -0.3, 0.0, 0.0, 0.0, 0.0])
+    f0 = K.project(q0, K.TARGETS[nf])
+    dq_ref = -0.2 * np.linalg.pinv(X0.reshape(m, 6)) @ (f0 - np.asarray(desired[:m]))
+    for mode in (L.MODE_DENSE, L.MODE_BLOCKDIAG):
+        p = E.filter_params(METHODS["KF"], nf, mode=mode)
+        cfg = E.closed_loop_cfg(p, E.noise_params(L.NOISE_NONE), T=3, dt=0.05, ibvs_gain=0.2, q_start=list(q0),
+                                desired_f=desired, change_q_start=False)
+        B = 5
+        out = E.closed_loop(cfg, 0, B, want_log=True, X0_in=E.dev(np.repeat(X0[None], B, 0)))
+        log = out["log"].cpu().numpy()
+        assert np.all(out["flags"].cpu().numpy() & L.FLAG_RANK_DEFICIENT)
+        for b in range(B):
+            dq0 = (log[b, 1, 0:6] - log[b, 0, 0:6]) / 0.05                 # frame 0: H = 0, the filter leaves X0 untouched
+            assert rel_err(dq0, dq_ref) <= 1e-8, (nf, mode, b, dq0, dq_ref)

@@ -52,6 +52,20 @@ def main():
                                     desired_f=DESIRED[nf], change_q_start=False)
             E.twist_loop(cfg, E.twist_cfg(x0_mode=L.X0_IMAGE_JACOBIAN, focal_x0=512.0, focal=512.0), 0, B, want_log=True,
                          want_state=True)
+    # zero initial Jacobian: the pseudo-inverse meets a rank-deficient Gram matrix on the first frames, so the cooperative
+    # Jacobi fallback (pinv_fallback_coop: dense M = 6, block-diagonal M >= 6, twist) and the serial one (dense M = 8) run
+    for nf in (4, 3):
+        m, N = 2 * nf, 12 * nf
+        X0 = torch.zeros(B, N, dtype=torch.float64, device="cuda")
+        for mode in (L.MODE_DENSE, L.MODE_BLOCKDIAG):
+            p = E.filter_params(L.METHOD_KF, nf, mode=mode)
+            cfg = E.closed_loop_cfg(p, noise, T=T, dt=0.05, ibvs_gain=0.2, q_start=Q_START, desired_f=DESIRED[nf])
+            out = E.closed_loop(cfg, 0, B, X0_in=X0)
+            assert int((out["flags"] & L.FLAG_RANK_DEFICIENT).ne(0).sum()) == B
+        p = E.filter_params(L.METHOD_KF, nf, mode=L.MODE_DENSE)
+        cfg = E.closed_loop_cfg(p, noise, T=T, dt=0.05, ibvs_gain=0.3, q_start=Q_START, desired_f=DESIRED[nf])
+        out = E.twist_loop(cfg, E.twist_cfg(x0_mode=L.X0_ZEROS), 0, B)
+        assert int((out["flags"] & L.FLAG_RANK_DEFICIENT).ne(0).sum()) == B
     q = torch.randn(B, 6, dtype=torch.float64, device="cuda")
     E.ur10_fk(q); E.project(4, q); E.initial_guess(4, q); E.noise_fill(noise, 0, B, T, 8); E.start_poses(Q_START, 5, True, 0, B)
     J = torch.randn(B, 8, 6, dtype=torch.float64, device="cuda")

@@ -273,6 +273,7 @@ __global__ void __launch_bounds__(128, UVS_BD_MINB) bd_closed_loop_kernel(const 
     constexpr int WPC = 4;
     __shared__ __align__(16) double sJ[WPC][GPW][M * 6];
     __shared__ __align__(16) double sSc[WPC][GPW][56];
+    __shared__ __align__(16) double sBig[(M >= 6) ? WPC : 1][(M >= 6) ? GPW : 1][(M >= 6) ? 72 : 2];   // Jacobi fallback work matrices
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, gl = lane % GS, grp = lane / GS;
     const long long warp_id = (long long)blockIdx.x * WPC + warp;
     const long long n_warps = (long long)gridDim.x * WPC;
@@ -383,7 +384,7 @@ __global__ void __launch_bounds__(128, UVS_BD_MINB) bd_closed_loop_kernel(const 
             __syncwarp();
             double x[6];
             int ib_flags = 0;
-            pinv_group<M, GS>(Jg, kappa * (f_new - desired), sc, gl, x, ib_flags);
+            pinv_group<M, GS>(Jg, kappa * (f_new - desired), sc, gl, x, ib_flags, (M >= 6) ? sBig[(M >= 6) ? warp : 0][(M >= 6) ? grp : 0] : nullptr);
             bool bad = false;
             double dq_new[6];
 #pragma unroll

@@ -54,8 +54,9 @@ struct alignas(16) DenseWS {
     double Kt[M * LD];
     double Ut[M * LD];
     double X[N];
-    double S[M * M];
-    double D[M * M];
+    double S[M * M];                            // S then D: >= 72 contiguous doubles for M >= 6, free once the gain is built:
+    double D[M * M];                            // the work matrices of the cooperative pseudo-inverse fallback
+    __device__ __forceinline__ double* jacobi_scratch() { return (M >= 6) ? S : nullptr; }
     double ib[56];                              // weights / IBVS scratch (G 21, g 6, b 8, res 8, x 6)
     double nu[M + (M & 1)];                     // innovation, read back by every lane
     double Lc[M * (M + 1) / 2 + ((M * (M + 1) / 2) & 1)];   // chol(S), packed lower, reciprocal diagonal
@@ -309,7 +310,7 @@ UVS_DEV void rank_update(PBlock& pb, double* Pd, const double* Kt, const double*
 // latency gaps with update FMAs.  Same results as rank_update() followed by pinv_warp().
 template <int M>
 UVS_DEV void ibvs_with_rank_update(PBlock& pb, double* Pd, const double* Kt, const double* Ut, const double* J,
-                                   double b_lane, double* sc, int lane, double (&x)[6], int& flags) {
+                                   double b_lane, double* sc, int lane, double (&x)[6], int& flags, double* big) {
     static_assert(M >= 6, "M < 6 uses the J J^T path of pinv_group");
     constexpr int K = 6;
     constexpr int C1 = M / 4, C2 = (3 * M) / 4, C3 = M - 1;      // k ranges handed to the four stages
@@ -384,7 +385,8 @@ UVS_DEV void ibvs_with_rank_update(PBlock& pb, double* Pd, const double* Kt, con
     __syncwarp();
     if (!ok) {
         flags |= UVS_FLAG_RANK_DEFICIENT;
-        if (lane == 0) pinv_fallback(M, J, sb, sx);
+        if (big != nullptr) pinv_fallback_coop<32>(M, J, sg, big, sx, lane);
+        else if (lane == 0) pinv_fallback(M, J, sb, sx);
     }
     __syncwarp();
     if (!ok) {

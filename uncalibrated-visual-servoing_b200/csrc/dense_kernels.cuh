@@ -250,11 +250,11 @@ __global__ void UVS_DENSE_BOUNDS dense_closed_loop_kernel(const __grid_constant_
             int ib_flags = 0;
             if constexpr (M >= 6 && !MCKF) {
                 if (so.rank_pending)
-                    ibvs_with_rank_update<M>(pb, w.Pd, w.Kt, w.Ut, w.X, kappa * (f_l - desired), w.ib, lane, x, ib_flags);
+                    ibvs_with_rank_update<M>(pb, w.Pd, w.Kt, w.Ut, w.X, kappa * (f_l - desired), w.ib, lane, x, ib_flags, w.jacobi_scratch());
                 else
-                    pinv_warp<M>(w.X, kappa * (f_l - desired), w.ib, lane, x, ib_flags);
+                    pinv_warp<M>(w.X, kappa * (f_l - desired), w.ib, lane, x, ib_flags, w.jacobi_scratch());
             } else {
-                pinv_warp<M>(w.X, kappa * (f_l - desired), w.ib, lane, x, ib_flags);
+                pinv_warp<M>(w.X, kappa * (f_l - desired), w.ib, lane, x, ib_flags, w.jacobi_scratch());
             }
             flags_all |= ib_flags;
             double dq_l = 0.0;

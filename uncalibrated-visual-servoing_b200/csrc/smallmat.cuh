@@ -158,6 +158,85 @@ static __device__ __noinline__ void pinv_fallback(int MM, const double* J, const
     }
 }
 
+// The same fallback for the 6 x 6 Gram case (MM >= 6), run by the GS lanes of a group together with both work matrices in
+// shared memory (`big`: 72 doubles, A then V) instead of one lane's local memory: the rotation sequence and every formula
+// are those of pinv_fallback (same results), but the three 6-long update loops of a rotation are one step of six lanes,
+// so it is ~4x faster — the 3-feature scene's square Jacobian passes near its singular configurations under impulsive
+// noise with KF / IMCC-KF and this path then runs on a sizeable share of the frames.  rhs = J^T b is read from `g`
+// (6 doubles, already computed by the fast path), the result goes to `x_out` (6 doubles, shared).  Every lane of the
+// group must call; `gl` = lane index inside the group.
+template <int GS>
+static __device__ __noinline__ void pinv_fallback_coop(int MM, const double* J, const double* g, double* big, double* x_out,
+                                                       int gl) {
+    constexpr int K = 6;
+    static_assert(GS >= K, "one lane per row of the Gram matrix");
+    const int lane = threadIdx.x & 31;
+    const unsigned mask = (GS == 32) ? 0xffffffffu : (((1u << (GS & 31)) - 1u) << ((lane / GS) * GS));
+    double* A = big;
+    double* V = big + 36;
+    __syncwarp(mask);
+    for (int e = gl; e < 36; e += GS) {
+        const int i = e / 6, j = e % 6;
+        double acc = 0.0;
+        for (int r = 0; r < MM; ++r) acc += J[r * 6 + i] * J[r * 6 + j];
+        A[e] = acc;
+        V[e] = (i == j) ? 1.0 : 0.0;
+    }
+    __syncwarp(mask);
+    const int k = gl < K ? gl : K - 1;                 // lanes >= 6 shadow lane 5 and do not store
+    const bool own = gl < K;
+    for (int sweep = 0; sweep < 30; ++sweep) {
+        double off = 0.0, diag = 0.0;
+        for (int i = 0; i < K; ++i) {
+            diag += A[i * 6 + i] * A[i * 6 + i];
+            for (int j = 0; j < i; ++j) off += A[i * 6 + j] * A[i * 6 + j];
+        }
+        if (!(off > 1e-40 * diag)) break;              // uniform in the group: every lane read the same values
+        for (int p = 0; p < K - 1; ++p)
+            for (int q = p + 1; q < K; ++q) {
+                const double apq = A[p * 6 + q];
+                if (apq == 0.0) continue;              // uniform
+                const double theta = (A[q * 6 + q] - A[p * 6 + p]) / (2.0 * apq);
+                const double t = copysign(1.0, theta) / (fabs(theta) + sqrt(theta * theta + 1.0));
+                const double c = rsqrt(t * t + 1.0), sn = t * c;
+                // columns p, q of row k (A and V)
+                const double akp = A[k * 6 + p], akq = A[k * 6 + q];
+                const double vkp = V[k * 6 + p], vkq = V[k * 6 + q];
+                __syncwarp(mask);                       // all reads of this rotation's inputs are done
+                if (own) {
+                    A[k * 6 + p] = c * akp - sn * akq;
+                    A[k * 6 + q] = sn * akp + c * akq;
+                    V[k * 6 + p] = c * vkp - sn * vkq;
+                    V[k * 6 + q] = sn * vkp + c * vkq;
+                }
+                __syncwarp(mask);
+                // rows p, q, column k
+                const double apk = A[p * 6 + k], aqk = A[q * 6 + k];
+                __syncwarp(mask);
+                if (own) {
+                    A[p * 6 + k] = c * apk - sn * aqk;
+                    A[q * 6 + k] = sn * apk + c * aqk;
+                }
+                __syncwarp(mask);
+            }
+    }
+    double lmax = 0.0;
+    for (int i = 0; i < K; ++i) lmax = fmax(lmax, A[i * 6 + i]);
+    const double cut = 64.0 * 2.220446049250313e-16 * lmax;
+    double y = 0.0;
+    for (int e = 0; e < K; ++e) {
+        const double lam = A[e * 6 + e];
+        if (!(lam > cut) || !(lmax > 0.0)) continue;
+        double proj = 0.0;
+        for (int i = 0; i < K; ++i) proj += V[i * 6 + e] * g[i];
+        proj /= lam;
+        y += V[k * 6 + e] * proj;
+    }
+    __syncwarp(mask);
+    if (own) x_out[k] = y;
+    __syncwarp(mask);
+}
+
 // Cooperative minimum-norm least squares x = pinv(J) b  (experiment.py:312) by a group of GS lanes
 // (GS = 32: one problem per warp; GS = 8 or 2: several problems per warp, the block-diagonal family).
 // J: [M x 6] row-major in shared memory; b_lane: b_j on group lane j < M; sc: >= 56 doubles of
@@ -165,9 +244,11 @@ static __device__ __noinline__ void pinv_fallback(int MM, const double* J, const
 // Fast path: Cholesky of the smaller Gram matrix (J^T J for M >= 6, J J^T for M < 6) + one step of
 // iterative refinement on the residual (corrected semi-normal equations, error ~ eps cond(J)); if a
 // Cholesky pivot is <= 1e-13 trace(Gram) (cond(J) >~ 3e6) group lane 0 runs pinv_fallback.
-// Result in x on every lane of the group.
+// Result in x on every lane of the group.  big: optional 72 doubles of per-group shared scratch; when given (and
+// M >= 6) the fallback runs cooperatively (pinv_fallback_coop) instead of on group lane 0.
 template <int M, int GS>
-UVS_DEV void pinv_group(const double* J, double b_lane, double* sc, int gl, double (&x)[6], int& flags) {
+UVS_DEV void pinv_group(const double* J, double b_lane, double* sc, int gl, double (&x)[6], int& flags,
+                        double* big = nullptr) {
     double* sG = sc;          // 21
     double* sg = sc + 21;     // 6
     double* sb = sc + 27;     // 8
@@ -279,7 +360,8 @@ UVS_DEV void pinv_group(const double* J, double b_lane, double* sc, int gl, doub
     __syncwarp();
     if (!ok) {
         flags |= UVS_FLAG_RANK_DEFICIENT;
-        if (gl == 0) pinv_fallback(M, J, sb, sx);
+        if (M >= 6 && GS >= 6 && big != nullptr) pinv_fallback_coop<(GS >= 6 ? GS : 32)>(M, J, sg, big, sx, gl);
+        else if (gl == 0) pinv_fallback(M, J, sb, sx);
     }
     __syncwarp();
     if (!ok) {
@@ -290,8 +372,9 @@ UVS_DEV void pinv_group(const double* J, double b_lane, double* sc, int gl, doub
 }
 
 template <int M>
-UVS_DEV void pinv_warp(const double* J, double b_lane, double* sc, int lane, double (&x)[6], int& flags) {
-    pinv_group<M, 32>(J, b_lane, sc, lane, x, flags);
+UVS_DEV void pinv_warp(const double* J, double b_lane, double* sc, int lane, double (&x)[6], int& flags,
+                       double* big = nullptr) {
+    pinv_group<M, 32>(J, b_lane, sc, lane, x, flags, big);
 }
 
 }  // namespace uvs

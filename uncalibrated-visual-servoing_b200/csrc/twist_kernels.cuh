@@ -27,6 +27,7 @@ struct TwistArgs {
 
 struct alignas(16) TwistWS {
     double Jg[36];          // geometric Jacobian, row-major (rows v;w, columns joints)
+    double jac[72];         // work matrices of the cooperative pseudo-inverse fallback (wrist singularities)
 };
 
 template <int M, bool MCKF>
@@ -232,10 +233,10 @@ __global__ void __launch_bounds__(kTwistThreads, 2) twist_closed_loop_kernel(con
             double x[6];
             int ib_flags = 0;
             if constexpr (DEFER) {
-                if (rank_pending) ibvs_with_rank_update<M>(pb, w.Pd, w.Kt, w.Ut, w.X, kappa * e_l, w.ib, lane, x, ib_flags);
-                else pinv_warp<M>(w.X, kappa * e_l, w.ib, lane, x, ib_flags);
+                if (rank_pending) ibvs_with_rank_update<M>(pb, w.Pd, w.Kt, w.Ut, w.X, kappa * e_l, w.ib, lane, x, ib_flags, w.jacobi_scratch());
+                else pinv_warp<M>(w.X, kappa * e_l, w.ib, lane, x, ib_flags, w.jacobi_scratch());
             } else {
-                pinv_warp<M>(w.X, kappa * e_l, w.ib, lane, x, ib_flags);
+                pinv_warp<M>(w.X, kappa * e_l, w.ib, lane, x, ib_flags, w.jacobi_scratch());
             }
             double dp[6];
 #pragma unroll
@@ -249,7 +250,7 @@ __global__ void __launch_bounds__(kTwistThreads, 2) twist_closed_loop_kernel(con
             }
             double dq[6];
             int jg_flags = 0;
-            pinv_warp<6>(ts.Jg, dx_l, w.ib, lane, dq, jg_flags);
+            pinv_warp<6>(ts.Jg, dx_l, w.ib, lane, dq, jg_flags, ts.jac);
             flags_all |= ib_flags | jg_flags;
 
             bool bad = false;
