@@ -385,8 +385,9 @@ UVS_DEV void ibvs_with_rank_update(PBlock& pb, double* Pd, const double* Kt, con
     __syncwarp();
     if (!ok) {
         flags |= UVS_FLAG_RANK_DEFICIENT;
-        if (big != nullptr) pinv_fallback_coop<32>(M, J, sg, big, sx, lane);
-        else if (lane == 0) pinv_fallback(M, J, sb, sx);
+        // always the cooperative version here: the lane-0 pinv_fallback() returned a wrong command when called from this
+        // function at M = 8 (test_closed_loop_rank_deficient_start_uses_the_fallback)
+        pinv_fallback_coop<32>(M, J, sg, big, sx, lane);
     }
     __syncwarp();
     if (!ok) {
