@@ -172,3 +172,20 @@ def test_run_sweep_fails_loudly_without_gpu():
         pytest.skip("CUDA present")
     with pytest.raises(uvs_b200._lib.UvsError):
         sweep.run_sweep(_config(**{"estimator.method": "GMCKF"}), epoch=1)
+
+
+def test_published_tables_parse_and_servo_rate():
+    """tools/published_comparison.py reads the reference's published ITAE curves from BASELINE.md (3 figures x 4 series x
+    12 noise levels); oracle.closed_loop.servo_rate is the plant model both oracles and the kernels share."""
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import published_comparison as pc
+    from oracle import closed_loop as CL
+    pub = pc.published_tables(os.path.join(ROOT, "BASELINE.md"))
+    assert sorted(pub) == ["results1", "results2", "results3"]
+    for fig, series in pub.items():
+        assert set(series) == set(pc.SERIES[fig]["runs"]) and all(len(v) == 12 for v in series.values())
+    assert pub["results2"]["RMCKF"][0] == (233102.0, 355742.0) and pub["results3"]["RMCKF (σ = 1)"][11][0] == 238561.0
+    cfg = dict(dt=0.05, v_max=1.0, a_max=4.0, servo_gain=0.5)
+    v = CL.servo_rate(cfg, np.array([4.0, -0.1, 0.3]), np.array([0.0, 0.0, 0.2]))
+    assert np.allclose(v, [0.2, -0.05, 0.15])          # lag 0.5, then |dv| <= a_max dt = 0.2, then |v| <= 1
+    assert np.allclose(CL.servo_rate(dict(dt=0.05), np.array([3.0]), np.array([0.0])), [3.0])      # no limits: kinematic
