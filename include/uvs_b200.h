@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define UVS_ABI_VERSION 3
+#define UVS_ABI_VERSION 4
 
 /* experiment.py:6-11 (Method).  RMCKF is the paper's name for GMCKF. */
 enum { UVS_METHOD_ANALYTICAL = 1, UVS_METHOD_KF = 2, UVS_METHOD_MCKF = 3,
@@ -57,8 +57,11 @@ enum { UVS_P_DENSE = 0,         /* [B, N, N]                                    
 /* per-frame flags (bit-or); epoch count of the MCKF fixed point in bits 8.. */
 #define UVS_FLAG_SKIP_SINGULAR   1   /* MCKF: a measurement weight underflowed to 0 -> correction skipped (experiment.py:233-236) */
 #define UVS_FLAG_SKIP_MAXEPOCH   2   /* MCKF: fpi_epoch_max reached -> correction skipped (experiment.py:246-248) */
-#define UVS_FLAG_CX_SINGULAR     4   /* MCKF: a state weight underflowed (the reference raises out of run() at experiment.py:224) */
-#define UVS_FLAG_NOT_SPD         8   /* Cholesky of P or S met a non-positive pivot -> correction skipped */
+#define UVS_FLAG_CX_SINGULAR     4   /* MCKF: a state weight underflowed (the reference raises out of run() at experiment.py:224);
+                                        closed loops: the trial ends UVS_STATUS_FAIL on that frame */
+#define UVS_FLAG_NOT_SPD         8   /* Cholesky of P or S met a non-positive pivot (P0, Q, R must be SPD, so this means non-finite
+                                        arithmetic): correction skipped; closed loops: the trial ends UVS_STATUS_FAIL on that frame,
+                                        as the reference does through np.linalg.pinv raising on the NaN state (experiment.py:312-316) */
 #define UVS_FLAG_RANK_DEFICIENT 16   /* IBVS: Jacobian numerically rank deficient, eigen fallback used */
 #define UVS_FLAG_NONFINITE      32   /* trial failed: non-finite state / command (experiment.py:312-316) */
 #define UVS_FLAG_OUT_OF_VIEW    64   /* trial failed: a feature left the field of view (utils.py:73-78 -> NaN centroid) */
@@ -140,6 +143,17 @@ typedef struct uvs_closed_loop_io {
     const double* X0_in;     /* optional [B,N] initial state replacing experiment.py:86-117 */
     int32_t p_layout;        /* UVS_P_* of P_out                                           */
     int32_t reserved;
+    /* Per-frame trace of the closed loop (ABI 4) — the open-loop replay gate of the closed-loop kernels themselves:
+     * with dq_in the command stream of a recorded run REPLACES the command the IBVS law computed (as the regressor of
+     * the next frame, experiment.py:188, and in the joint integration, experiment.py:320), so frame k of the kernel
+     * sees the recorded run's inputs and its X / P / dq / kappa can be compared frame by frame (1e-9) with what the
+     * reference computed; the computed command is still what dq_log receives.  All optional. */
+    const double* dq_in;     /* [B,T,6] recorded commands; ignored by uvs_twist_loop (its regressor is dp)  */
+    double*  X_log;          /* [B,T,N] state after the update of frame k (experiment.py:300)              */
+    double*  P_log;          /* [B,T,m,6,6] diagonal 6x6 blocks of the covariance after the update of frame k */
+    double*  dq_log;         /* [B,T,6] command computed in frame k (experiment.py:312; twist loop: joint rates) */
+    double*  kappa_log;      /* [B,T,m] weights kappa of frame k (experiment.py:306-308)                   */
+    int32_t* flags_log;      /* [B,T] per-frame flags | epochs << UVS_FLAG_EPOCH_SHIFT                     */
 } uvs_closed_loop_io;
 
 /* The camera-twist pipeline of the reference's tests/ scripts (tests/{ibvs,kalman,mckf}_{1,3,4}_feature(s).py):
@@ -158,7 +172,11 @@ typedef struct uvs_twist_cfg {
     int32_t x0_mode;         /* UVS_X0_*; io->X0_in replaces the state but not the first f_old     */
     int32_t depth_mode;      /* UVS_DEPTH_* used by the interaction matrix                        */
     int32_t dp_zero_mask;    /* bit i set: dp[i] = 0 after the control law (kalman_3_features.py:139-141) */
-    int32_t reserved;
+    int32_t stale_fk;        /* 1: R06 and J_geom of the START pose are used in every frame — what kalman_4_features.py:165-169
+                                and mckf_{1,3,4}_feature(s).py do: they call getCameraRotation() / jacobian() without
+                                recalculate_fkine, and UR10Simulation only refreshes its cached transforms on
+                                fkine(recalculate=True) (ur10_simulation.py:97-110,141-144); 0: the pose of the frame
+                                (kalman_{1,3}_feature(s).py:133/142 and ibvs_*.py refresh it every frame) */
     double focal_x0;         /* focal length of the initial guess (kalman_4_features.py:85: 1024)  */
     double focal;            /* focal length of the UVS_METHOD_ANALYTICAL interaction matrix (ibvs_4_features.py:81) */
     double err_threshold;    /* frames run while ||f - f*||_2 > err_threshold (kalman_4_features.py:111); < 0: all T */
@@ -242,7 +260,7 @@ int uvs_closed_loop_host(const uvs_closed_loop_cfg* cfg, uint64_t trial0, int64_
  * statistic s in {ISE,IAE,ITAE}: sums[c][s] = {n_ok, sum x, sum x^2} over
  * SUCCESS trials, plus n_fail[c].  level = (trial0+b) / sweep_epoch (clamped).
  * sums [n_levels,3,3] and n_fail [n_levels] are ACCUMULATED into (zero them
- * first); they are what is all-reduced across GPUs. */
+ * first); they are what is all-reduced across GPUs.  1 <= n_levels <= 512. */
 int uvs_reduce_stats(int64_t B, uint64_t trial0, int32_t sweep_epoch, int32_t n_levels,
                      const double* stats, const int32_t* status, double* sums, double* n_fail,
                      void* stream);

@@ -52,11 +52,17 @@ def in_view(f, z):
                 and np.all(z > 0.01))
 
 
-def run_trial(cfg, trial, noise=None, q0=None, x0=None, record=False):
+def run_trial(cfg, trial, noise=None, q0=None, x0=None, record=False, dq_in=None):
     """Returns dict(status, frames, stats[3], q_log, f_log, noise_log, t_log, ...).
 
     noise: optional [T,m] precomputed stream (else Philox from cfg);
-    q0 / x0: optional overrides of the start pose / initial state.
+    q0 / x0: optional overrides of the start pose / initial state;
+    dq_in: optional [T,6] recorded command stream that replaces the computed command after every frame
+    (uvs_closed_loop_io.dq_in: the replay gate of the closed-loop kernels); dq_log keeps the computed one.
+
+    A frame on which the reference raises out of Experiment.run() — np.linalg.inv(Cx) with a zero weight
+    (experiment.py:224), np.linalg.cholesky(P) (:203), a singular innovation covariance outside GMCKF's try
+    block (:192, :238, :264) — ends the trial with FAIL, as the CUDA kernels do (csrc/common.cuh abort_flags).
     """
     nf = cfg["nf"]
     m, N = 2 * nf, 12 * nf
@@ -95,6 +101,7 @@ def run_trial(cfg, trial, noise=None, q0=None, x0=None, record=False):
     P_log = [] if record else None
     flags_log = np.zeros(T, dtype=np.int64); epoch_log = np.zeros(T, dtype=np.int64)
     status = SUCCESS
+    abort_flags = 0
     dq = np.zeros(6)
     v_prev = np.zeros(6)
     k = 0
@@ -109,14 +116,23 @@ def run_trial(cfg, trial, noise=None, q0=None, x0=None, record=False):
         Z = f - f_old
         h = np.zeros(6) if k_it == 0 else dq         # experiment.py:183-188
         sigma = filters.annealed_bw(cfg["kernel_bw"], cfg["annealing"], k_it, T)
-        if structured:
-            X, Pb, K, kappa, info = filters.step_blockdiag(
-                method, X, Pb, h, Z, qd, rd, sigma, cfg["fpi_threshold"], cfg["fpi_epoch_max"],
-                cfg["joseph"], cfg["mckf_skip"])
-        else:
-            X, P, K, kappa, info = filters.step_dense(
-                method, X, P, h, Z, Q, R, sigma, cfg["fpi_threshold"], cfg["fpi_epoch_max"],
-                cfg["joseph"], cfg["mckf_skip"])
+        try:
+            if structured:
+                X, Pb, K, kappa, info = filters.step_blockdiag(
+                    method, X, Pb, h, Z, qd, rd, sigma, cfg["fpi_threshold"], cfg["fpi_epoch_max"],
+                    cfg["joseph"], cfg["mckf_skip"])
+            else:
+                X, P, K, kappa, info = filters.step_dense(
+                    method, X, P, h, Z, Q, R, sigma, cfg["fpi_threshold"], cfg["fpi_epoch_max"],
+                    cfg["joseph"], cfg["mckf_skip"])
+        except np.linalg.LinAlgError:            # cholesky(P) / inv(S): raised outside every try block of run()
+            status = FAIL
+            abort_flags = filters.FLAG_NOT_SPD
+            break
+        if info["flags"] & filters.FLAG_CX_SINGULAR:     # experiment.py:224 raises out of run()
+            status = FAIL
+            abort_flags = filters.FLAG_CX_SINGULAR
+            break
         try:
             dq, _ = ibvs.ibvs_step(X, f, desired, kappa, cfg["ibvs_gain"])
         except np.linalg.LinAlgError:
@@ -132,11 +148,13 @@ def run_trial(cfg, trial, noise=None, q0=None, x0=None, record=False):
             X_log[k] = X
             P_log.append(Pb.copy() if structured else P.copy())
         k += 1
+        if dq_in is not None:
+            dq = np.asarray(dq_in[k_it], dtype=float)
         v_prev = servo_rate(cfg, dq, v_prev)
         q = q + v_prev * dt                                       # experiment.py:320,335 (v = dq without limits)
     out = dict(status=status, frames=k, q_log=q_log[:k], f_log=f_log[:k], noise_log=noise_log[:k],
                t_log=t_log[:k], kernel_bw_log=bw_log[:k], dq_log=dq_log[:k],
-               flags_log=flags_log[:k], epoch_log=epoch_log[:k], X=X,
+               flags_log=flags_log[:k], epoch_log=epoch_log[:k], X=X, abort_flags=abort_flags,
                P=(Pb if structured else P))
     out["stats"] = stats_mod.trial_stats(out["t_log"], out["f_log"], desired)
     if record:

@@ -39,6 +39,7 @@ class FakeRobot:
         self.q = np.zeros(6)
         self.q_cmd = np.zeros(6)
         self.steps = 0
+        self._Ts = None                       # cached T_0_1 .. T_0_6 (ur10_simulation.py:59,97-110)
         self.snapshots = [] if snapshot else None
 
     # -- clock: frame k is seen at t_k = (k+1)*dt, exactly n_frames frames ---------------------
@@ -56,6 +57,7 @@ class FakeRobot:
         self.q_cmd = self.q.copy()
         self.steps = 0
         self.step()
+        self.fkine(recalculate=True)          # ur10_simulation.py:59
 
     def stop(self):
         pass
@@ -82,27 +84,35 @@ class FakeRobot:
                 self.snapshots.append(snap)
 
     # -- ur10_simulation.py:97-195 ------------------------------------------------------------
+    # UR10Simulation caches T_0_1 .. T_0_6 and refreshes them ONLY in fkine(recalculate=True) (which first reads the
+    # joints, :98-99); jacobian / getCameraRotation / getCameraPosition / getCameraHeight / computeZ pass their
+    # recalculate_fkine flag on and otherwise work on the cache; computePose never touches it (it asks the simulator,
+    # :156-168).  start() ends with fkine(recalculate=True) (:59).  Scripts that call robot.jacobian() /
+    # getCameraRotation() without the flag therefore use the pose of the last refresh, not the current one.
     def fkine(self, recalculate=False, all_transforms=False):
-        Ts = kinematics.fkine_all(self.q)
-        return tuple(reversed(Ts)) if all_transforms else Ts[-1]
+        if recalculate or self._Ts is None:
+            self._Ts = kinematics.fkine_all(self.q)
+        return tuple(reversed(self._Ts)) if all_transforms else self._Ts[-1]
 
     def jacobian(self, recalculate_fkine=False):
-        return kinematics.jacobian(self.q)
+        self.fkine(recalculate=recalculate_fkine)
+        return kinematics.jacobian_from_transforms(self._Ts)
 
     def getCameraRotation(self, recalculate_fkine=False):
-        return kinematics.fkine(self.q)[0:3, 0:3]
+        return self.fkine(recalculate=recalculate_fkine)[0:3, 0:3]
 
     def getCameraPosition(self, recalculate_fkine=False):
-        return kinematics.fkine(self.q)[0:3, 3]
+        return self.fkine(recalculate=recalculate_fkine)[0:3, 3]
 
     def getCameraHeight(self, recalculate_fkine=False):
-        return kinematics.fkine(self.q)[2, 3]
+        return self.fkine(recalculate=recalculate_fkine)[2, 3]
 
     def computePose(self, recalculate_fkine=False):
-        return kinematics.camera_pose(self.q)
+        return kinematics.camera_pose(self.q)            # simulator query: always the current pose
 
     def computeZ(self, n=1, recalculate_fkine=False):
-        return kinematics.compute_Z(self.q, self.targets[:n])
+        cam = self.getCameraPosition(recalculate_fkine)
+        return np.array([np.linalg.norm(cam - pw) for pw in self.targets[:n]])
 
     def getCameraImage(self):
         f = kinematics.project(self.q, self.targets)

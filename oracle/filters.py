@@ -18,6 +18,7 @@ ANALYTICAL, KF, MCKF, IMCCKF, GMCKF = 1, 2, 3, 4, 5
 FLAG_SKIP_SINGULAR = 1   # experiment.py:233-236 / :292-294
 FLAG_SKIP_MAXEPOCH = 2   # experiment.py:246-248
 FLAG_CX_SINGULAR = 4     # experiment.py:224 raises out of run() in the reference
+FLAG_NOT_SPD = 8         # include/uvs_b200.h: a Cholesky of P or S met a non-positive pivot
 
 
 def gaussian_kernel(e, bw):

@@ -72,7 +72,12 @@ def fkine(q):
 
 def jacobian(q):
     """Geometric Jacobian, ur10_simulation.py:112-139."""
-    Ts = fkine_all(q)
+    return jacobian_from_transforms(fkine_all(q))
+
+
+def jacobian_from_transforms(Ts):
+    """The same from a given list T_0_1 .. T_0_6 — UR10Simulation.jacobian() works on its CACHED transforms, which are
+    only refreshed by fkine(recalculate=True) (ur10_simulation.py:97-115)."""
     p_e = Ts[5][0:3, 3]
     z = [np.array([0.0, 0.0, 1.0])] + [Ts[i][0:3, 2] for i in range(5)]
     p = [np.zeros(3)] + [Ts[i][0:3, 3] for i in range(5)]

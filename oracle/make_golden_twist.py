@@ -59,17 +59,17 @@ SCRIPTS = {
         dp_zero_mask=0b011100, square_inv=True)),
     "kalman_4_features": dict(nf=4, max_frames=440, cfg=dict(
         method=filters.KF, gain=0.5, x0_mode=TL.X0_IMAGE_JACOBIAN, focal_x0=1024.0, joseph=True,
-        err_threshold=0.01)),
+        err_threshold=0.01, stale_fk=True)),
     "mckf_1_feature": dict(nf=1, max_frames=400, cfg=dict(
         method=filters.MCKF, gain=0.001, desired_f=[128.0, 128.0], x0_mode=TL.X0_RANDOM, joseph=True,
-        err_threshold=0.01, kernel_bw=200.0, fpi_threshold=0.01, fpi_epoch_max=100, mckf_skip=False)),
+        err_threshold=0.01, kernel_bw=200.0, fpi_threshold=0.01, fpi_epoch_max=100, mckf_skip=False, stale_fk=True)),
     "mckf_3_features": dict(nf=3, max_frames=300, cfg=dict(
         method=filters.MCKF, gain=0.001, x0_mode=TL.X0_RANDOM, joseph=True, square_inv=True,
-        err_threshold=0.01, kernel_bw=200.0, fpi_threshold=0.01, fpi_epoch_max=100, mckf_skip=False)),
+        err_threshold=0.01, kernel_bw=200.0, fpi_threshold=0.01, fpi_epoch_max=100, mckf_skip=False, stale_fk=True)),
     "mckf_4_features": dict(nf=4, max_frames=300, cfg=dict(
         method=filters.MCKF, gain=0.5, x0_mode=TL.X0_IMAGE_JACOBIAN,
         focal_x0=256.0 / (2.0 * np.tan(0.5 * 0.65)), joseph=True, err_threshold=0.01, kernel_bw=20.0,
-        fpi_threshold=0.01, fpi_epoch_max=100, mckf_skip=False)),
+        fpi_threshold=0.01, fpi_epoch_max=100, mckf_skip=False, stale_fk=True)),
 }
 
 

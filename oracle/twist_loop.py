@@ -33,6 +33,10 @@ DEFAULTS = dict(
     desired_f=[149.0, 145.0, 125.0, 121.0, 101.0, 145.0, 125.0, 169.0],
     x0_mode=X0_IMAGE_JACOBIAN, focal_x0=1024.0, focal=kinematics.FOCAL, depth_mode=DEPTH_DISTANCE,
     err_threshold=-1.0, dp_zero_mask=0, square_inv=False,
+    # True: R06 and J_geom of the START pose in every frame — kalman_4_features.py:165-169 and mckf_{1,3,4}_feature(s).py call
+    # getCameraRotation() / jacobian() without recalculate_fkine, and UR10Simulation only refreshes its cached transforms
+    # in fkine(recalculate=True) (ur10_simulation.py:97-110); the other five scripts refresh every frame
+    stale_fk=False,
     kernel_bw=20.0, fpi_threshold=0.01, fpi_epoch_max=100, annealing=False, joseph=True, mckf_skip=False,
     noise_type=0, noise_params={}, hold_cnt=0,
     noise_seed=123456, pose_seed=12345, change_q_start=False, targets=None, P0=None, Q=None, R=None,
@@ -73,7 +77,8 @@ def depths(q, targets, depth_mode):
 
 
 def twist_to_joint_rates(q, dp):
-    """dx = kron(I2, R06^T) dp ; dq = pinv(J_geom) dx   (kalman_4_features.py:168-172)."""
+    """dx = kron(I2, R06^T) dp ; dq = pinv(J_geom) dx   (kalman_4_features.py:168-172); q = the pose the robot object's
+    cached transforms were last refreshed at."""
     R = kinematics.fkine(q)[0:3, 0:3]
     dx = np.kron(np.eye(2), R.T) @ np.asarray(dp, dtype=float).reshape(6, 1)
     return (np.linalg.pinv(kinematics.jacobian(q)) @ dx).ravel()
@@ -117,6 +122,7 @@ def run_trial(cfg, trial=0, noise=None, q0=None, x0=None, record=False):
     status = SUCCESS
     dp = np.zeros(6)
     v_prev = np.zeros(6)
+    q_fk = q.copy()                                          # pose of the last fkine(recalculate=True): the start pose
     error = np.ones(m)                                       # kalman_4_features.py:70
     k = 0
     for k_it in range(T):
@@ -144,7 +150,7 @@ def run_trial(cfg, trial=0, noise=None, q0=None, x0=None, record=False):
             for i in range(6):
                 if cfg["dp_zero_mask"] >> i & 1:
                     dp[i] = 0.0                              # kalman_3_features.py:139-141
-            dq = twist_to_joint_rates(q, dp)
+            dq = twist_to_joint_rates(q_fk if cfg.get("stale_fk") else q, dp)
         except np.linalg.LinAlgError:
             status = FAIL
             break

@@ -27,23 +27,24 @@ def test_every_declared_symbol_is_exported(lib):
     for name in declared:
         assert hasattr(handle, name), name
     assert declared == set(lib.EXPORTED)
-    assert handle.uvs_version() == 3
+    assert handle.uvs_version() == 4
 
 
 def test_struct_layout_matches_c(lib, tmp_path):
     src = tmp_path / "sz.c"
     src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "uvs_b200.h"\n'
-                   'int main(){printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu %zu\\n", sizeof(uvs_filter_params), sizeof(uvs_noise_params),'
+                   'int main(){printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu\\n", sizeof(uvs_filter_params), sizeof(uvs_noise_params),'
                    'sizeof(uvs_closed_loop_cfg), sizeof(uvs_closed_loop_io), offsetof(uvs_closed_loop_cfg, sweep),'
                    'offsetof(uvs_closed_loop_cfg, P0), offsetof(uvs_closed_loop_io, p_layout), sizeof(uvs_twist_cfg),'
-                   'offsetof(uvs_twist_cfg, err_threshold), offsetof(uvs_closed_loop_cfg, servo_gain));return 0;}\n')
+                   'offsetof(uvs_twist_cfg, err_threshold), offsetof(uvs_closed_loop_cfg, servo_gain),'
+                   'offsetof(uvs_closed_loop_io, flags_log), offsetof(uvs_twist_cfg, stale_fk));return 0;}\n')
     exe = tmp_path / "sz"
     subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)])
     got = [int(v) for v in subprocess.check_output([str(exe)]).split()]
     want = [C.sizeof(lib.FilterParams), C.sizeof(lib.NoiseParams), C.sizeof(lib.ClosedLoopCfg),
             C.sizeof(lib.ClosedLoopIO), lib.ClosedLoopCfg.sweep.offset, lib.ClosedLoopCfg.P0.offset,
             lib.ClosedLoopIO.p_layout.offset, C.sizeof(lib.TwistCfg), lib.TwistCfg.err_threshold.offset,
-            lib.ClosedLoopCfg.servo_gain.offset]
+            lib.ClosedLoopCfg.servo_gain.offset, lib.ClosedLoopIO.flags_log.offset, lib.TwistCfg.stale_fk.offset]
     assert got == want
 
 
@@ -80,7 +81,7 @@ def test_twist_loop_validates_before_touching_the_device(lib):
     """uvs_twist_loop / uvs_closed_loop reject bad scalar arguments with UVS_ERR_INVALID (no CUDA call is needed to say so)."""
     handle = lib.load()
     cfg, tw, io = lib.ClosedLoopCfg(), lib.TwistCfg(), lib.ClosedLoopIO()
-    cfg.filt.method, cfg.filt.nf, cfg.filt.joseph, cfg.T = 2, 4, 1, 10
+    cfg.filt.method, cfg.filt.nf, cfg.filt.joseph, cfg.T, cfg.dt = 2, 4, 1, 10, 0.05
     io.stats, io.status = 8, 8                                   # never dereferenced on the error paths below
     tw.x0_mode, tw.focal_x0, tw.focal = 7, 1.0, 1.0
     assert handle.uvs_twist_loop(C.byref(cfg), C.byref(tw), 0, 1, C.byref(io), None) == -1
@@ -99,3 +100,17 @@ def test_twist_loop_validates_before_touching_the_device(lib):
     cfg.filt.mode, cfg.filt.method = 0, 1                        # ANALYTICAL is a twist-loop method, not a closed-loop one
     assert handle.uvs_closed_loop(C.byref(cfg), 0, 1, C.byref(io), None) == -1 and "method" in lib.last_error()
     assert handle.uvs_twist_loop(C.byref(cfg), C.byref(tw), 0, 0, C.byref(io), None) == 0      # empty batch: no-op
+    # range checks that used to fail silently inside the kernels (NaN weights, frozen filters): ADVICE r01
+    cfg.filt.method = 5
+    for field, bad, word in (("dt", 0.0, "dt"), ("sweep_param", 3, "sweep_param")):
+        old = getattr(cfg, field)
+        setattr(cfg, field, bad)
+        assert handle.uvs_closed_loop(C.byref(cfg), 0, 1, C.byref(io), None) == -1 and word in lib.last_error()
+        setattr(cfg, field, old)
+    cfg.filt.kernel_bw = 0.0
+    assert handle.uvs_closed_loop(C.byref(cfg), 0, 1, C.byref(io), None) == -1 and "kernel_bw" in lib.last_error()
+    cfg.filt.kernel_bw, cfg.filt.method, cfg.filt.fpi_epoch_max = 10.0, 3, 0
+    assert handle.uvs_closed_loop(C.byref(cfg), 0, 1, C.byref(io), None) == -1 and "fpi_epoch_max" in lib.last_error()
+    cfg.filt.fpi_epoch_max, cfg.sweep_len, cfg.sweep_epoch = 10, 12, 0
+    assert handle.uvs_closed_loop(C.byref(cfg), 0, 1, C.byref(io), None) == -1 and "sweep_epoch" in lib.last_error()
+    assert handle.uvs_reduce_stats(1, 0, 1, 513, 8, 8, 8, 8, None) == -1 and "n_levels" in lib.last_error()

@@ -119,6 +119,83 @@ def test_closed_loop_matches_reference(uvs, name, mode):
         assert rel_err(out["X"].cpu().numpy()[0], g["X"][T - 1]) <= 1e-6
 
 
+@pytest.mark.parametrize("name", RUNS)
+@pytest.mark.parametrize("mode", ["dense", "blockdiag"])
+def test_closed_loop_kernel_replay_gate(uvs, name, mode):
+    """The 1e-9 per-step gate on the closed-loop kernels THEMSELVES (north star: "J-hat and P within 1e-9 per step on
+    replayed inputs").  uvs_closed_loop is fed the reference run's noise log and start pose and, through io.dq_in, the
+    reference's own command stream, so frame k executes on the reference's inputs — in the dense family this is the
+    instantiation bench.py times (Q = R = NULL + Joseph: dense_closed_loop_kernel<8, METHOD, FAST> = dense_step<..., DEFER,
+    FAST> + ibvs_with_rank_update, bandwidth table, bounded sincos, fast_div).  X every frame, the diagonal blocks of P on
+    the stored frames, kappa and the command the kernel computed, all against experiment.py's own values."""
+    L, E = uvs._lib, uvs.engine
+    g = load_golden(f"ref_run_{name}.npz")
+    T = int(g["frames"])
+    p = _fp(uvs, g, L.MODE_DENSE if mode == "dense" else L.MODE_BLOCKDIAG)
+    cfg = E.closed_loop_cfg(p, E.noise_params(L.NOISE_NONE), T=300, dt=0.05, ibvs_gain=0.2, q_start=g["q_start"],
+                            desired_f=[149.0, 145.0, 125.0, 121.0, 101.0, 145.0, 125.0, 169.0], change_q_start=False)
+    B = 2
+    rep = lambda a: E.dev(np.repeat(np.asarray(a)[None], B, 0))          # noqa: E731
+    out = E.closed_loop(cfg, 0, B, want_log=True, want_trace=True, noise_in=rep(g["noise_log"]), q0_in=rep(g["q_start"]),
+                        dq_in=rep(g["dq"]))
+    assert out["status"].tolist() == [int(g["status"])] * B and out["frames"].tolist() == [T] * B
+    X_log, P_log, dq_log, kap, fl = (out[k].cpu().numpy() for k in ("X_log", "P_log", "dq_log", "kappa_log", "flags_log"))
+    log = out["log"].cpu().numpy()
+    for b in range(B):
+        # the plant followed the recorded commands: joints and noisy features of the reference, frame by frame
+        assert rel_err(log[b, :, 0:6], g["q_log"]) <= 1e-12 and rel_err(log[b, :, 6:14], g["f_log"]) <= 1e-12
+        ex = [rel_err(X_log[b, k], g["X"][k]) for k in range(T)]
+        assert max(ex) <= TOL_STEP, (name, mode, b, int(np.argmax(ex)), max(ex))
+        ep = [rel_err(P_log[b, k], g["P"][j]) for j, k in enumerate(g["p_frames"])]
+        assert max(ep) <= TOL_STEP, (name, mode, b, max(ep))
+        # the command of every frame (pinv in place: cond(J) reaches ~600 in these runs, SURVEY 7)
+        ed = [rel_err(dq_log[b, k], g["dq"][k]) for k in range(T)]
+        assert max(ed) <= 1e-8, (name, mode, b, int(np.argmax(ed)), max(ed))
+    if str(g["method"]) == "GMCKF":
+        assert rel_err(kap[0], g["kappa"]) <= TOL_STEP
+    skipped = (fl[0] & (L.FLAG_SKIP_SINGULAR | L.FLAG_SKIP_MAXEPOCH | L.FLAG_CX_SINGULAR)) != 0
+    assert np.array_equal(skipped, g["skip"] != 0)
+    if str(g["method"]) == "MCKF":
+        assert np.array_equal(fl[0] >> L.FLAG_EPOCH_SHIFT, g["epoch"])
+    assert np.array_equal(X_log[0], X_log[B - 1])
+
+
+@pytest.mark.parametrize("method", ["KF", "IMCCKF", "GMCKF", "MCKF"])
+@pytest.mark.parametrize("nf", [1, 3])
+def test_closed_loop_kernel_replay_gate_small_scenes(uvs, nf, method):
+    """Same gate for the 1- and 3-feature scenes (M = 2, 6; experiment.py itself is hard-wired to 8 measurements, so the
+    recorded run is the oracle's as-written restatement): fast instantiation of the dense family and the block family."""
+    from oracle import closed_loop as CL, noise_model as NM
+    L, E = uvs._lib, uvs.engine
+    m = 2 * nf
+    desired = {1: [128.0, 128.0], 3: [153.5, 144.5, 125.5, 116.5, 99.5, 144.5]}[nf]
+    q0 = np.array([0.0, -np.pi / 8, np.pi / 2 + np.pi / 8, 0.0, -np.pi / 2, 0.0])
+    T = 120
+    ocfg = CL.make_cfg(method=METHODS[method], nf=nf, t_max=T * 0.05, desired_f=desired, q_start=list(q0), ibvs_gain=0.05,
+                       change_q_start=False, annealing=(method != "KF"), noise_type=NM.GAUSSIAN_MIXTURE,
+                       noise_params=dict(std=1.0, mean=30.0, rho=0.1), noise_seed=31 + nf)
+    ref = CL.run_trial(ocfg, 3, record=True)
+    assert ref["frames"] == T and ref["status"] == 0
+    for mode in (L.MODE_DENSE, L.MODE_BLOCKDIAG):
+        p = E.filter_params(METHODS[method], nf, mode=mode, annealing=(method != "KF"))
+        cfg = E.closed_loop_cfg(p, E.noise_params(L.NOISE_NONE), T=T, dt=0.05, ibvs_gain=0.05, q_start=list(q0),
+                                desired_f=desired, change_q_start=False)
+        out = E.closed_loop(cfg, 0, 1, want_trace=True, noise_in=E.dev(ref["noise_log"][None]),
+                            dq_in=E.dev(ref["dq_log"][None]))
+        X_log, P_log, dq_log = (out[k].cpu().numpy()[0] for k in ("X_log", "P_log", "dq_log"))
+        assert int(out["frames"][0]) == T
+        ex = [rel_err(X_log[k], ref["X_log"][k]) for k in range(T)]
+        assert max(ex) <= TOL_STEP, (nf, method, mode, int(np.argmax(ex)), max(ex))
+        from oracle import filters as F
+        ep = [rel_err(P_log[k], F.blocks_of(ref["P_log"][k], m)) for k in range(T)]
+        assert max(ep) <= TOL_STEP, (nf, method, mode, max(ep))
+        if nf == 1:      # 3 features: the square Jacobian is inverted near its singular poses; the command is checked at M = 2, 8
+            ed = [rel_err(dq_log[k], ref["dq_log"][k]) for k in range(T)]
+            assert max(ed) <= 1e-8, (nf, method, mode, int(np.argmax(ed)), max(ed))
+        fl = out["flags_log"].cpu().numpy()[0]
+        assert np.array_equal(fl >> L.FLAG_EPOCH_SHIFT, ref["epoch_log"])
+
+
 def test_out_of_view_start_fails_like_reference(uvs):
     L, E = uvs._lib, uvs.engine
     g = load_golden("ref_run_kf_nominal_fov.npz")
@@ -130,6 +207,44 @@ def test_out_of_view_start_fails_like_reference(uvs):
         out = E.closed_loop(cfg, 0, 2)
         assert out["status"].tolist() == [1, 1] and out["frames"].tolist() == [0, 0]
         assert int(out["flags"][0]) & L.FLAG_OUT_OF_VIEW
+
+
+@pytest.mark.parametrize("method", ["KF", "MCKF", "IMCCKF", "GMCKF"])
+def test_error_paths_end_the_trial_like_the_reference(uvs, method):
+    """Which status a trial ends with on the reference's error paths (experiment.py:203, 224-236, 292-294, 312-316), pinned
+    against the oracle's closed loop for both kernel families:
+      * a NaN measurement at frame k0 turns X (or S) non-finite; the reference's np.linalg.pinv raises on it and run()
+        returns FAIL with k0 logged frames — the kernels stop on the same frame (flags NONFINITE or NOT_SPD);
+      * a finite 1e6-pixel outlier: MCKF's measurement weight underflows to 0 -> "Cy is singular, skipping correction
+        step" (experiment.py:233-236), the trial goes on; RMCKF's 1e-6 regulariser absorbs it; KF swallows it."""
+    from oracle import closed_loop as CL
+    L, E = uvs._lib, uvs.engine
+    g = load_golden("ref_run_kf_white.npz")
+    k0 = 7
+    ocfg = CL.make_cfg(method=METHODS[method], annealing=False, change_q_start=False, q_start=list(g["q_start"]))
+    for kind in ("nan", "outlier"):
+        noise = g["noise_log"].copy()
+        noise[k0, 2] = np.nan if kind == "nan" else 1e6
+        ref = CL.run_trial(ocfg, 0, noise=noise)
+        for mode in (L.MODE_DENSE, L.MODE_BLOCKDIAG):
+            p = E.filter_params(METHODS[method], 4, mode=mode)
+            cfg = E.closed_loop_cfg(p, E.noise_params(L.NOISE_NONE), T=300, dt=0.05, ibvs_gain=0.2, q_start=g["q_start"],
+                                    desired_f=ocfg["desired_f"], change_q_start=False)
+            out = E.closed_loop(cfg, 0, 2, want_trace=True, noise_in=E.dev(np.repeat(noise[None], 2, 0)))
+            status, frames, flags = (out[k].cpu().numpy() for k in ("status", "frames", "flags"))
+            fl = out["flags_log"].cpu().numpy()[0]
+            if kind == "nan":
+                assert ref["status"] == 1 and ref["frames"] == k0
+                assert status.tolist() == [1, 1] and frames.tolist() == [k0, k0], (method, mode, status, frames)
+                assert flags[0] & (L.FLAG_NONFINITE | L.FLAG_NOT_SPD)
+            else:
+                assert status[0] == ref["status"], (method, mode)
+                if ref["status"] == 0:
+                    assert frames[0] == ref["frames"] == 300
+                skipped = bool(fl[k0] & L.FLAG_SKIP_SINGULAR)
+                assert skipped == bool(ref["flags_log"][k0] & 1) if ref["frames"] > k0 else True
+                if method == "MCKF":
+                    assert skipped                                    # experiment.py:233-236
 
 
 # ------------------------------------------------------------------ kinematics / IBVS / noise
@@ -198,6 +313,50 @@ def test_ibvs_rank_deficient(uvs):
         assert rel_err(dq[b], ref) <= 1e-7, b
     assert flags[0] & L.FLAG_RANK_DEFICIENT and flags[1] & L.FLAG_RANK_DEFICIENT and flags[2] & L.FLAG_RANK_DEFICIENT
     assert flags[3] == 0
+
+
+@pytest.mark.parametrize("nf", [1, 3, 4])
+def test_ibvs_matches_numpy_pinv_across_conditioning(uvs, nf):
+    """cond(J) from 1e2 to 1e14 and beyond the cut: the command must follow np.linalg.pinv (experiment.py:312: SVD, singular
+    values <= 1e-15 sigma_max dropped).  Above cond ~ 3e6 the kernels leave the Cholesky path for one-sided Jacobi on J
+    itself; a Gram-matrix eigen-fallback (round 1) truncated singular values below ~1e-7 sigma_max where numpy still
+    inverts them.  Tolerance: two backward-stable solvers agree to ~ eps cond(J) (consistent right-hand sides: b in
+    range(J) for the overdetermined 8 x 6 case, where a residual would add a cond^2 term)."""
+    E, L = uvs.engine, uvs._lib
+    m = 2 * nf
+    k = min(m, 6)
+    rng = np.random.default_rng(100 + nf)
+    conds = [1e2, 1e4, 1e6, 1e7, 1e8, 1e9, 1e10, 1e12, 1e14]
+    Js, bs, cs = [], [], []
+    for cond in conds:
+        for rep in range(8):
+            U, _ = np.linalg.qr(rng.standard_normal((m, m)))
+            V, _ = np.linalg.qr(rng.standard_normal((6, 6)))
+            sv = np.geomspace(1.0, 1.0 / cond, k) * rng.uniform(5.0, 50.0)
+            J = (U[:, :k] * sv) @ V[:, :k].T
+            b = J @ rng.standard_normal(6) if m > 6 else rng.standard_normal(m) * 10
+            Js.append(J); bs.append(b); cs.append(cond)
+    J, b = np.stack(Js), np.stack(bs)
+    dq, flags = E.ibvs(nf, E.dev(J), E.dev(b), None, 1.0)
+    dq, flags = dq.cpu().numpy(), flags.cpu().numpy()
+    worst = {}
+    for i, cond in enumerate(cs):
+        ref = -np.linalg.pinv(J[i]) @ b[i]
+        err = rel_err(dq[i], ref)
+        worst[cond] = max(worst.get(cond, 0.0), err)
+        assert err <= max(1e-9, 200 * 2.2e-16 * cond), (nf, cond, err)
+        if cond >= 1e8:
+            assert flags[i] & L.FLAG_RANK_DEFICIENT            # the rank-revealing path ran
+            assert np.linalg.norm(dq[i]) > 1e-3 * np.linalg.norm(ref)      # ... and did not truncate what numpy inverts
+    # beyond numpy's cutoff both sides drop the direction: sigma_min = 1e-17 sigma_max
+    U, _ = np.linalg.qr(rng.standard_normal((m, m)))
+    V, _ = np.linalg.qr(rng.standard_normal((6, 6)))
+    sv = np.ones(k); sv[-1] = 1e-17
+    Jc = (U[:, :k] * sv) @ V[:, :k].T
+    bc = rng.standard_normal(m)
+    dqc, _ = E.ibvs(nf, E.dev(Jc[None]), E.dev(bc[None]), None, 1.0)
+    refc = -np.linalg.pinv(Jc) @ bc
+    assert np.linalg.norm(refc) < 1e3 and rel_err(dqc.cpu().numpy()[0], refc) <= 1e-9
 
 
 NOISE_CASES = [
@@ -536,17 +695,17 @@ def test_long_trials_without_bandwidth_table(uvs):
         assert rel_err(out["stats"].cpu().numpy()[0], ref["stats"]) <= 1e-6
 
 
-@pytest.mark.parametrize("nf", [3, 4])
+@pytest.mark.parametrize("nf", [1, 3, 4])
 def test_closed_loop_rank_deficient_start_uses_the_fallback(uvs, nf):
     """A rank-1 initial Jacobian: the first command must be the minimum-norm solution np.linalg.pinv gives (experiment.py:312)
-    — computed by the cooperative Jacobi fallback (dense M = 6, block-diagonal) or the serial one (dense M = 8)."""
+    — computed inside the closed-loop kernels by the cooperative one-sided Jacobi fallback (every M, both families)."""
     from oracle import closed_loop as CL, kinematics as K
     L, E = uvs._lib, uvs.engine
     m, N = 2 * nf, 12 * nf
     rng = np.random.default_rng(nf)
     row = rng.standard_normal(6) * 50.0
     X0 = (np.outer(rng.uniform(0.5, 2.0, m), row)).reshape(N)           # every row parallel to `row`: rank 1
-    desired = [153.5, 144.5, 125.5, 116.5, 99.5, 144.5] if nf == 3 else CL.DEFAULTS["desired_f"]
+    desired = {1: [128.0, 128.0], 3: [153.5, 144.5, 125.5, 116.5, 99.5, 144.5], 4: CL.DEFAULTS["desired_f"]}[nf]
     q0 = np.array(CL.DEFAULTS["q_start"]) + np.array([0.0, -0.3, 0.0, 0.0, 0.0, 0.0])
     f0 = K.project(q0, K.TARGETS[nf])
     dq_ref = -0.2 * np.linalg.pinv(X0.reshape(m, 6)) @ (f0 - np.asarray(desired[:m]))

@@ -52,7 +52,8 @@ def gpu_cfg(uvs, ocfg, *, P0=None, Q=None, R=None, noise=None):
                             desired_f=ocfg["desired_f"], change_q_start=ocfg["change_q_start"],
                             pose_seed=ocfg["pose_seed"], P0=P0)
     tw = E.twist_cfg(x0_mode=ocfg["x0_mode"], depth_mode=ocfg["depth_mode"], dp_zero_mask=ocfg["dp_zero_mask"],
-                     focal_x0=ocfg["focal_x0"], focal=ocfg["focal"], err_threshold=ocfg["err_threshold"])
+                     focal_x0=ocfg["focal_x0"], focal=ocfg["focal"], err_threshold=ocfg["err_threshold"],
+                     stale_fk=ocfg.get("stale_fk", False))
     return cfg, tw
 
 
@@ -196,3 +197,29 @@ def test_twist_loop_servo_limits(uvs):
         assert np.abs(np.diff(ref["q_log"], axis=0)).max() <= 0.05 * 0.05 * (1 + 1e-12)
         assert rel_err(log[b, :k, :6], ref["q_log"]) <= TOL
         assert rel_err(log[b, :k, 6:14], ref["f_log"]) <= TOL
+
+
+@pytest.mark.parametrize("nf", [1, 3, 4])
+def test_twist_loop_rank_deficient_jacobian(uvs, nf):
+    """A rank-1 estimated Jacobian in the twist pipeline: dp = -GAIN pinv(J) e must be numpy's minimum-norm solution
+    (kalman_4_features.py:160) — the cooperative one-sided Jacobi fallback inside twist_closed_loop_kernel, every M."""
+    from oracle import twist_loop
+    L, E = uvs._lib, uvs.engine
+    m, N = 2 * nf, 12 * nf
+    rng = np.random.default_rng(40 + nf)
+    X0 = np.outer(rng.uniform(0.5, 2.0, m), rng.standard_normal(6) * 300.0).reshape(N)
+    desired = {1: [128.0, 128.0], 3: [153.5, 144.5, 125.5, 116.5, 99.5, 144.5]}.get(nf)
+    over = dict(method=2, nf=nf, T=3, gain=0.05, x0_mode=0)
+    if desired:
+        over["desired_f"] = desired
+    ocfg = twist_loop.make_cfg(**over)
+    cfg, tw = gpu_cfg(uvs, ocfg)
+    out = E.twist_loop(cfg, tw, 0, 3, want_log=True, X0_in=E.dev(np.repeat(X0[None], 3, 0)))
+    ref = twist_loop.run_trial(ocfg, 0, noise=np.zeros((3, m)), x0=X0)
+    log = out["log"].cpu().numpy()
+    assert np.all(out["flags"].cpu().numpy() & L.FLAG_RANK_DEFICIENT)
+    # frame 0 runs on X0 untouched (dp = 0 regressor): the first joint step is pinv(J_geom) R pinv(X0) e
+    for b in range(3):
+        step = log[b, 1, :6] - log[b, 0, :6]
+        step_ref = ref["q_log"][1] - ref["q_log"][0]
+        assert rel_err(step, step_ref) <= 1e-8, (nf, b, step, step_ref)

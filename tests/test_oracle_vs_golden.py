@@ -160,7 +160,7 @@ def twist_cfg_from_golden(g):
         key = str(key)
         if key in ("method", "x0_mode", "depth_mode", "dp_zero_mask", "fpi_epoch_max"):
             kw[key] = int(v)
-        elif key in ("joseph", "mckf_skip", "square_inv"):
+        elif key in ("joseph", "mckf_skip", "square_inv", "stale_fk"):
             kw[key] = bool(v)
         elif key == "desired_f":
             kw[key] = [float(x) for x in v]

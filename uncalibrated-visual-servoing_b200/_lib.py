@@ -51,12 +51,13 @@ class ClosedLoopCfg(C.Structure):
 class ClosedLoopIO(C.Structure):
     _fields_ = [("stats", _dp), ("status", _dp), ("frames", _dp), ("flags", _dp), ("log", _dp), ("X_out", _dp),
                 ("P_out", _dp), ("noise_in", _dp), ("q0_in", _dp), ("X0_in", _dp), ("p_layout", C.c_int32),
-                ("reserved", C.c_int32)]
+                ("reserved", C.c_int32), ("dq_in", _dp), ("X_log", _dp), ("P_log", _dp), ("dq_log", _dp),
+                ("kappa_log", _dp), ("flags_log", _dp)]
 
 
 class TwistCfg(C.Structure):
     _fields_ = [("x0_mode", C.c_int32), ("depth_mode", C.c_int32), ("dp_zero_mask", C.c_int32),
-                ("reserved", C.c_int32), ("focal_x0", C.c_double), ("focal", C.c_double),
+                ("stale_fk", C.c_int32), ("focal_x0", C.c_double), ("focal", C.c_double),
                 ("err_threshold", C.c_double)]
 
 

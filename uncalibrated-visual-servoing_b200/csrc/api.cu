@@ -88,14 +88,42 @@ int uvs_device_info(int* sm_count, int* cc_major, int* cc_minor, int* sm_clock_k
     return 0;
 }
 
+// range checks shared by the filter entry points: a zero bandwidth or epoch cap would not fail, it would turn every
+// kernel weight into NaN (1 / sigma^2 = inf) or skip every correction, and the trial would end FAIL / frozen silently
+static int check_filter(const uvs_filter_params& fp, bool needs_sigma) {
+    if (!valid_nf(fp.nf)) return set_error(UVS_ERR_INVALID, "nf must be 1, 3 or 4 (got %d)", fp.nf);
+    const bool mc = fp.method == UVS_METHOD_MCKF || fp.method == UVS_METHOD_IMCCKF || fp.method == UVS_METHOD_GMCKF;
+    if (mc && needs_sigma && !(fp.kernel_bw > 0.0) ) return set_error(UVS_ERR_INVALID, "kernel_bw must be > 0 (got %g)", fp.kernel_bw);
+    if (fp.method == UVS_METHOD_MCKF) {
+        if (fp.fpi_epoch_max < 1) return set_error(UVS_ERR_INVALID, "fpi_epoch_max must be >= 1 (got %d)", fp.fpi_epoch_max);
+        if (!(fp.fpi_threshold >= 0.0)) return set_error(UVS_ERR_INVALID, "fpi_threshold must be >= 0 (got %g)", fp.fpi_threshold);
+        if (!fp.joseph) return set_error(UVS_ERR_UNSUPPORTED, "MCKF requires the Joseph update (tests/mckf_*.py use it too)");
+    }
+    if (fp.mode < UVS_MODE_AUTO || fp.mode > UVS_MODE_BLOCKDIAG) return set_error(UVS_ERR_INVALID, "mode %d", fp.mode);
+    return 0;
+}
+
+static int check_loop_cfg(const uvs_closed_loop_cfg& c) {
+    if (c.T < 1) return set_error(UVS_ERR_INVALID, "T=%d", c.T);
+    if (!(c.dt > 0.0)) return set_error(UVS_ERR_INVALID, "dt must be > 0 (got %g)", c.dt);
+    if (c.sweep_len < 0 || c.sweep_len > UVS_MAX_SWEEP) return set_error(UVS_ERR_INVALID, "sweep_len");
+    if (c.sweep_param < 0 || c.sweep_param > 2) return set_error(UVS_ERR_INVALID, "sweep_param must be 0, 1 or 2 (got %d)", c.sweep_param);
+    if (c.sweep_len > 0 && c.sweep_epoch < 1) return set_error(UVS_ERR_INVALID, "sweep_epoch must be >= 1 (got %d)", c.sweep_epoch);
+    if (!(c.v_max >= 0.0) || !(c.a_max >= 0.0) || !(c.servo_gain >= 0.0))
+        return set_error(UVS_ERR_INVALID, "v_max / a_max / servo_gain must be >= 0");
+    return 0;
+}
+
 static int run_replay(ReplayArgs& a, void* stream) {
     const uvs_filter_params& fp = a.fp;
     if (!valid_nf(fp.nf)) return set_error(UVS_ERR_INVALID, "nf must be 1, 3 or 4 (got %d)", fp.nf);
     if (!valid_method(fp.method)) return set_error(UVS_ERR_INVALID, "method %d is not a filter method", fp.method);
     if (a.B < 0 || a.T < 1) return set_error(UVS_ERR_INVALID, "B=%lld T=%d", a.B, a.T);
     if (a.p_layout != UVS_P_DENSE && a.p_layout != UVS_P_BLOCKS) return set_error(UVS_ERR_INVALID, "p_layout");
-    if (!fp.joseph && fp.method == UVS_METHOD_MCKF)
-        return set_error(UVS_ERR_UNSUPPORTED, "MCKF requires the Joseph update (tests/mckf_*.py use it too)");
+    // single step: the bandwidth is the `sigma` argument; replay: kernel_bw (+ annealing)
+    if (int rc = check_filter(fp, !a.direct)) return rc;
+    const bool mc = fp.method != UVS_METHOD_KF;
+    if (a.direct && mc && !(a.sigma > 0.0)) return set_error(UVS_ERR_INVALID, "sigma must be > 0 (got %g)", a.sigma);
     if (a.B == 0) return 0;
     DeviceInfo d;
     if (int rc = device_info(d)) return rc;
@@ -197,12 +225,10 @@ int uvs_closed_loop(const uvs_closed_loop_cfg* cfg, uint64_t trial0, int64_t B,
     const uvs_filter_params& fp = cfg->filt;
     if (!valid_nf(fp.nf)) return set_error(UVS_ERR_INVALID, "nf must be 1, 3 or 4 (got %d)", fp.nf);
     if (!valid_method(fp.method)) return set_error(UVS_ERR_INVALID, "method %d is not a filter method", fp.method);
-    if (cfg->T < 1 || B < 0) return set_error(UVS_ERR_INVALID, "T=%d B=%lld", cfg->T, (long long)B);
-    if (cfg->sweep_len < 0 || cfg->sweep_len > UVS_MAX_SWEEP) return set_error(UVS_ERR_INVALID, "sweep_len");
-    if (!(cfg->v_max >= 0.0) || !(cfg->a_max >= 0.0) || !(cfg->servo_gain >= 0.0))
-        return set_error(UVS_ERR_INVALID, "v_max / a_max / servo_gain must be >= 0");
-    if (!fp.joseph && fp.method == UVS_METHOD_MCKF)
-        return set_error(UVS_ERR_UNSUPPORTED, "MCKF requires the Joseph update");
+    if (B < 0) return set_error(UVS_ERR_INVALID, "B=%lld", (long long)B);
+    if (int rc = check_loop_cfg(*cfg)) return rc;
+    if (int rc = check_filter(fp, true)) return rc;
+    if (io->p_layout != UVS_P_DENSE && io->p_layout != UVS_P_BLOCKS) return set_error(UVS_ERR_INVALID, "p_layout");
     if (int rc = check_noise(cfg->noise)) return rc;
     if (B == 0) return 0;
     DeviceInfo d;
@@ -229,18 +255,16 @@ int uvs_twist_loop(const uvs_closed_loop_cfg* cfg, const uvs_twist_cfg* tw, uint
     const uvs_filter_params& fp = cfg->filt;
     if (!valid_nf(fp.nf)) return set_error(UVS_ERR_INVALID, "nf must be 1, 3 or 4 (got %d)", fp.nf);
     if (fp.method != UVS_METHOD_ANALYTICAL && !valid_method(fp.method)) return set_error(UVS_ERR_INVALID, "method %d", fp.method);
-    if (cfg->T < 1 || B < 0) return set_error(UVS_ERR_INVALID, "T=%d B=%lld", cfg->T, (long long)B);
-    if (cfg->sweep_len < 0 || cfg->sweep_len > UVS_MAX_SWEEP) return set_error(UVS_ERR_INVALID, "sweep_len");
-    if (!(cfg->v_max >= 0.0) || !(cfg->a_max >= 0.0) || !(cfg->servo_gain >= 0.0))
-        return set_error(UVS_ERR_INVALID, "v_max / a_max / servo_gain must be >= 0");
+    if (B < 0) return set_error(UVS_ERR_INVALID, "B=%lld", (long long)B);
+    if (int rc = check_loop_cfg(*cfg)) return rc;
+    if (int rc = check_filter(fp, true)) return rc;
+    if (io->p_layout != UVS_P_DENSE && io->p_layout != UVS_P_BLOCKS) return set_error(UVS_ERR_INVALID, "p_layout");
     if (tw->x0_mode < UVS_X0_ZEROS || tw->x0_mode > UVS_X0_RANDOM) return set_error(UVS_ERR_INVALID, "x0_mode %d", tw->x0_mode);
     if (tw->depth_mode != UVS_DEPTH_DISTANCE && tw->depth_mode != UVS_DEPTH_HEIGHT) return set_error(UVS_ERR_INVALID, "depth_mode %d", tw->depth_mode);
     if (tw->dp_zero_mask < 0 || tw->dp_zero_mask > 63) return set_error(UVS_ERR_INVALID, "dp_zero_mask %d", tw->dp_zero_mask);
     if ((fp.method == UVS_METHOD_ANALYTICAL && !(tw->focal > 0.0)) ||
         (tw->x0_mode == UVS_X0_IMAGE_JACOBIAN && !(tw->focal_x0 > 0.0)))
         return set_error(UVS_ERR_INVALID, "focal lengths must be positive");
-    if (!fp.joseph && fp.method == UVS_METHOD_MCKF)
-        return set_error(UVS_ERR_UNSUPPORTED, "MCKF requires the Joseph update");
     if (fp.mode == UVS_MODE_BLOCKDIAG) return set_error(UVS_ERR_UNSUPPORTED, "the twist loop runs in the dense family only");
     if (int rc = check_noise(cfg->noise)) return rc;
     if (B == 0) return 0;
@@ -302,8 +326,9 @@ int uvs_closed_loop_host(const uvs_closed_loop_cfg* cfg, uint64_t trial0, int64_
 
 int uvs_reduce_stats(int64_t B, uint64_t trial0, int32_t sweep_epoch, int32_t n_levels,
                      const double* stats, const int32_t* status, double* sums, double* n_fail, void* stream) {
-    if (!sums || !n_fail || B < 0 || n_levels < 1 || n_levels > 4096 || (B > 0 && (!stats || !status)))
-        return set_error(UVS_ERR_INVALID, "uvs_reduce_stats: bad argument");
+    // n_levels * 80 B of shared memory per CTA: 512 levels stay under the 48 KB a kernel gets without opting in
+    if (!sums || !n_fail || B < 0 || n_levels < 1 || n_levels > 512 || (B > 0 && (!stats || !status)))
+        return set_error(UVS_ERR_INVALID, "uvs_reduce_stats: bad argument (1 <= n_levels <= 512)");
     if (B == 0) return 0;
     return check_cuda(launch_reduce_stats(B, trial0, sweep_epoch, n_levels, stats, status, sums, n_fail,
                                           (cudaStream_t)stream), "reduce_stats");

@@ -14,6 +14,7 @@ __global__ void ibvs_kernel(long long B, const double* J, const double* e, const
                             double* dq_out, int32_t* flags_out) {
     __shared__ __align__(16) double sJ[8][M * 6];
     __shared__ __align__(16) double sc[8][56];
+    __shared__ __align__(16) double sBig[8][(M >= 6) ? pinv_scratch_doubles(M) : 2];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     for (long long b = (long long)blockIdx.x * 8 + warp; b < B; b += (long long)gridDim.x * 8) {
         for (int i = lane; i < M * 6; i += 32) sJ[warp][i] = J[b * M * 6 + i];
@@ -22,7 +23,7 @@ __global__ void ibvs_kernel(long long B, const double* J, const double* e, const
         __syncwarp();
         double x[6];
         int flags = 0;
-        pinv_warp<M>(sJ[warp], bl, sc[warp], lane, x, flags);
+        pinv_warp<M>(sJ[warp], bl, sc[warp], lane, x, flags, sBig[warp]);
 #pragma unroll
         for (int r = 0; r < 6; ++r) if (lane == r) dq_out[b * 6 + r] = -gain * x[r];
         if (flags_out && lane == 0) flags_out[b] = flags;

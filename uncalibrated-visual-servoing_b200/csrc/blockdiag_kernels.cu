@@ -273,7 +273,7 @@ __global__ void __launch_bounds__(128, UVS_BD_MINB) bd_closed_loop_kernel(const 
     constexpr int WPC = 4;
     __shared__ __align__(16) double sJ[WPC][GPW][M * 6];
     __shared__ __align__(16) double sSc[WPC][GPW][56];
-    __shared__ __align__(16) double sBig[(M >= 6) ? WPC : 1][(M >= 6) ? GPW : 1][(M >= 6) ? 72 : 2];   // Jacobi fallback work matrices
+    __shared__ __align__(16) double sBig[(M >= 6) ? WPC : 1][(M >= 6) ? GPW : 1][(M >= 6) ? pinv_scratch_doubles(M) : 2];   // Jacobi fallback work matrices
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, gl = lane % GS, grp = lane / GS;
     const long long warp_id = (long long)blockIdx.x * WPC + warp;
     const long long n_warps = (long long)gridDim.x * WPC;
@@ -348,6 +348,8 @@ __global__ void __launch_bounds__(128, UVS_BD_MINB) bd_closed_loop_kernel(const 
         int status = UVS_STATUS_SUCCESS, frames = 0, flags_all = 0;
         bool alive = trial_ok;
         const double desired = cfg.desired_f[row];
+        const bool traced = a.io.X_log != nullptr || a.io.P_log != nullptr || a.io.dq_log != nullptr ||
+                            a.io.kappa_log != nullptr || a.io.flags_log != nullptr;
 
         for (int k = 0; k < T; ++k) {
             if (!__any_sync(UVS_FULL_MASK, alive)) break;
@@ -375,6 +377,9 @@ __global__ void __launch_bounds__(128, UVS_BD_MINB) bd_closed_loop_kernel(const 
             const double sigma = annealed_bw(cfg.filt.kernel_bw, cfg.filt.annealing, k, T);
             int flags = 0, epoch = 0;
             const double kappa = bd_step<GS, METHOD>(s, cfg.filt, h, z, sigma, own && alive, flags, epoch);
+            if (alive && (flags & kAbortFlags)) {                // the reference ends FAIL here (common.cuh)
+                alive = false; status = UVS_STATUS_FAIL; flags_all |= flags;
+            }
             // IBVS on the group's Jacobian
             __syncwarp();
             if (gl < M) {
@@ -409,6 +414,28 @@ __global__ void __launch_bounds__(128, UVS_BD_MINB) bd_closed_loop_kernel(const 
                     ise += e * e; iae += fabs(e); itae += t * fabs(e);
                 }
                 ++frames;
+                if (traced && trial_ok) {                                // per-frame trace (uvs_closed_loop_io, ABI 4)
+                    const size_t bt = (size_t)b * T + k;
+                    if (own) {
+                        if (a.io.X_log) {
+#pragma unroll
+                            for (int i = 0; i < 6; ++i) a.io.X_log[bt * N + 6 * gl + i] = s.x[i];
+                        }
+                        if (a.io.P_log) store_row_P(s, a.io.P_log + bt * (M * 36), UVS_P_BLOCKS, M, gl);
+                        if (a.io.kappa_log) a.io.kappa_log[bt * M + gl] = kappa;
+                    }
+                    if (gl == 0) {
+                        if (a.io.dq_log) {
+#pragma unroll
+                            for (int r = 0; r < 6; ++r) a.io.dq_log[bt * 6 + r] = dq_new[r];
+                        }
+                        if (a.io.flags_log) a.io.flags_log[bt] = flags | ib_flags | (epoch << UVS_FLAG_EPOCH_SHIFT);
+                    }
+                }
+                if (a.io.dq_in && trial_ok) {                            // replay gate: recorded command
+#pragma unroll
+                    for (int r = 0; r < 6; ++r) dq_new[r] = a.io.dq_in[((size_t)b * T + k) * 6 + r];
+                }
 #pragma unroll
                 for (int r = 0; r < 6; ++r) {
                     dq[r] = dq_new[r];

@@ -57,6 +57,7 @@ struct alignas(16) DenseWS {
     double S[M * M];                            // S then D: >= 72 contiguous doubles for M >= 6, free once the gain is built:
     double D[M * M];                            // the work matrices of the cooperative pseudo-inverse fallback
     __device__ __forceinline__ double* jacobi_scratch() { return (M >= 6) ? S : nullptr; }
+    static_assert(2 * M * M >= pinv_scratch_doubles(M), "S + D hold the work matrices of pinv_fallback_osj");
     double ib[56];                              // weights / IBVS scratch (G 21, g 6, b 8, res 8, x 6)
     double nu[M + (M & 1)];                     // innovation, read back by every lane
     double Lc[M * (M + 1) / 2 + ((M * (M + 1) / 2) & 1)];   // chol(S), packed lower, reciprocal diagonal
@@ -385,9 +386,7 @@ UVS_DEV void ibvs_with_rank_update(PBlock& pb, double* Pd, const double* Kt, con
     __syncwarp();
     if (!ok) {
         flags |= UVS_FLAG_RANK_DEFICIENT;
-        // always the cooperative version here: the lane-0 pinv_fallback() returned a wrong command when called from this
-        // function at M = 8 (test_closed_loop_rank_deficient_start_uses_the_fallback)
-        pinv_fallback_coop<32>(M, J, sg, big, sx, lane);
+        pinv_fallback_osj<32>(M, J, sb, big, sx, lane);
     }
     __syncwarp();
     if (!ok) {
@@ -775,33 +774,31 @@ UVS_DEV double dense_step(PBlock& pb, DenseWS<M, METHOD == UVS_METHOD_MCKF>& w, 
         return kappa;
     } else {
         // ------------------------------------------------------------------ MCKF (experiment.py:194-250)
+        // The first pass of the fixed point starts from X_corrected = X, so its state residuals are zero, Cx = I and
+        // P_hat = P: it needs neither chol(P) nor the weighted product, and its gain K = A (S0 + R_hat)^-1 has the
+        // form that lets the Joseph update collapse to the rank-M form P -= K U^T, U = A + K (R_hat - R).  With the
+        // reference's fpi_threshold = 0.1 ~96 % of the frames stop after that pass, so the 48 x 48 block
+        // Cholesky (N^3 / 3 flops, the dominant cost of this branch) is factored lazily, by the first frame that
+        // needs a second pass; the reference factors P every frame (experiment.py:203) but only uses the factor there.
         double nu[M];
 #pragma unroll
         for (int j = 0; j < M; j += 2) {
             const double2 t = *reinterpret_cast<const double2*>(w.nu + j);
             nu[j] = t.x; nu[j + 1] = t.y;
         }
-        // S0 of the TRUE predicted covariance is needed by the Joseph form
-        for (int e = lane; e < M * M; e += 32) {
-            const int i = e / M, k = e % M;
-            double s0 = 0.0;
-#pragma unroll
-            for (int r = 0; r < 6; ++r) s0 += h[r] * w.At[k * LD + 6 * i + r];
-            w.D[e] = s0;
-        }
-        const bool spd = block_cholesky<M>(pb, w.Pd, w.Lp, lane);
         for (int row = lane; row < N; row += 32) w.Xc[row] = w.X[row];
         __syncwarp();
-        if (!spd) {
-            out.flags |= UVS_FLAG_NOT_SPD;
-            return kappa;
-        }
+        double* ddiag = w.ib + 8;
         bool skip = false;
         int epoch = 0;
         double difference = INFINITY;
         while (difference > fp.fpi_threshold && epoch < fp.fpi_epoch_max) {
             const double* Ain = w.At;
             if (epoch > 0) {
+                if (epoch == 1) {                                       // Bp = chol(P^-), experiment.py:203
+                    const bool spd = block_cholesky<M>(pb, w.Pd, w.Lp, lane);
+                    if (!spd) { out.flags |= UVS_FLAG_NOT_SPD; skip = true; break; }
+                }
                 // ex = Bp^-1 (X - Xc) ; cx = G(ex)
                 for (int row = lane; row < N; row += 32) w.dx[row] = w.X[row] - w.Xc[row];
                 __syncwarp();
@@ -835,7 +832,9 @@ UVS_DEV double dense_step(PBlock& pb, DenseWS<M, METHOD == UVS_METHOD_MCKF>& w, 
             if (__any_sync(UVS_FULL_MASK, cy == 0.0)) {                 // experiment.py:231-236
                 out.flags |= UVS_FLAG_SKIP_SINGULAR; skip = true; break;
             }
-            const bool ok = build_and_factor_S<M>(Ain, h, cc, 1.0 / cy, false, 1.0, w.S, w.ib, nullptr, nullptr, 0, 0.0, L, lane, r_id);
+            // first pass: also D = R_hat - R for the rank-M Joseph form (w.D / ddiag)
+            const bool ok = build_and_factor_S<M>(Ain, h, cc, 1.0 / cy, false, 1.0, w.S, w.ib, w.D, ddiag,
+                                                  epoch == 0 ? 1 : 0, 0.0, L, lane, r_id);
             if (!ok) { out.flags |= UVS_FLAG_NOT_SPD; skip = true; break; }
             // K rows, X_corrected = X + K (Z - H X)        experiment.py:238-242
             double num = 0.0, den = 0.0;
@@ -863,7 +862,39 @@ UVS_DEV double dense_step(PBlock& pb, DenseWS<M, METHOD == UVS_METHOD_MCKF>& w, 
         }
         out.epoch = epoch;
         if (skip) return kappa;
-        // X = X_corrected ; Joseph with the last K:  V = A - K (S0 + R)/2
+        if (epoch == 1) {
+            // X = X_corrected ; one pass: K = A S^-1, so P = P^- - K U^T with U = A + K (R_hat - R)
+            for (int row = lane; row < N; row += 32) {
+                w.X[row] = w.Xc[row];
+                double kr[M];
+#pragma unroll
+                for (int k = 0; k < M; ++k) kr[k] = w.Kt[k * LD + row];
+#pragma unroll
+                for (int k = 0; k < M; ++k) {
+                    double u = w.At[k * LD + row];
+                    if (r_id) u += kr[k] * ddiag[k];
+                    else {
+#pragma unroll
+                        for (int j = 0; j < M; ++j) u += kr[j] * w.D[j * M + k];
+                    }
+                    w.Ut[k * LD + row] = u;
+                }
+            }
+            __syncwarp();
+            rank_update<M, false>(pb, w.Pd, w.Kt, w.Ut, lane);
+            __syncwarp();
+            return kappa;
+        }
+        // several passes: the last gain is not of the form A S^-1; Joseph as the symmetric rank-2M update with
+        // V = A - K (S0 + R)/2, S0 = H A of the TRUE predicted covariance
+        for (int e = lane; e < M * M; e += 32) {
+            const int i = e / M, k = e % M;
+            double s0 = 0.0;
+#pragma unroll
+            for (int r = 0; r < 6; ++r) s0 += h[r] * w.At[k * LD + 6 * i + r];
+            w.D[e] = s0;
+        }
+        __syncwarp();
         for (int row = lane; row < N; row += 32) {
             w.X[row] = w.Xc[row];
             double kr[M];
@@ -916,6 +947,25 @@ __device__ void init_consts(DenseConsts<M>& cc, const uvs_filter_params& fp) {
             for (int k = c; k < i; ++k) v -= cc.Br[i * M + k] * cc.Brinv[k * M + c];
             cc.Brinv[i * M + c] = v / cc.Br[i * M + i];
         }
+}
+
+// Per-frame trace of a closed-loop kernel (uvs_closed_loop_io, ABI 4): the state / covariance / command / weights of
+// frame k of trial b.  Called after the covariance update of the frame has completed (it is deferred into the IBVS
+// pseudo-inverse on the fast path).  `traced` is warp-uniform and false in production launches.
+UVS_DEV bool io_traced(const uvs_closed_loop_io& io) {
+    return io.X_log != nullptr || io.P_log != nullptr || io.dq_log != nullptr || io.kappa_log != nullptr || io.flags_log != nullptr;
+}
+
+template <int M>
+UVS_DEV void trace_frame(const uvs_closed_loop_io& io, size_t bt, const double* Pd, const double* X,
+                         double dq_l, double kappa, int flags, int lane) {
+    constexpr int N = 6 * M;
+    if (io.X_log) for (int r = lane; r < N; r += 32) io.X_log[bt * N + r] = X[r];
+    if (io.P_log)           // diagonal blocks only (UVS_P_BLOCKS): a copy out of shared memory, no register traffic
+        for (int e = lane; e < M * 36; e += 32) io.P_log[bt * (M * 36) + e] = Pd[(e / 36) * kBlkStride + e % 36];
+    if (io.dq_log && lane < 6) io.dq_log[bt * 6 + lane] = dq_l;
+    if (io.kappa_log && lane < M) io.kappa_log[bt * M + lane] = kappa;
+    if (io.flags_log && lane == 0) io.flags_log[bt] = flags;
 }
 
 }  // namespace uvs

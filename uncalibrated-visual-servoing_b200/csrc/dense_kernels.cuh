@@ -187,6 +187,7 @@ __global__ void UVS_DENSE_BOUNDS dense_closed_loop_kernel(const __grid_constant_
 
         constexpr int FB = 32 / M;         // frames of noise drawn at once: lane = slot * M + coordinate
         const bool philox = (a.io.noise_in == nullptr) && (cfg.noise.type != UVS_NOISE_NONE);
+        const bool traced = io_traced(a.io);
         double fresh_batch = 0.0;
         for (int k = 0; k < T; ++k) {
             // ---- plant: joint angles -> this lane's feature coordinate ------------------------------
@@ -244,6 +245,7 @@ __global__ void UVS_DENSE_BOUNDS dense_closed_loop_kernel(const __grid_constant_
                 kappa = dense_step<M, METHOD, (M >= 6 && !MCKF), FAST>(pb, w, cc, cfg.filt, h, z, sigma, lane, so, inv_s2);
             }
             flags_all |= so.flags;
+            if (so.flags & kAbortFlags) { status = UVS_STATUS_FAIL; break; }      // the reference ends FAIL here (common.cuh)
 
             // IBVS: dq = -gain pinv(J) (kappa o error)                    experiment.py:300-312
             double x[6];
@@ -278,6 +280,9 @@ __global__ void UVS_DENSE_BOUNDS dense_closed_loop_kernel(const __grid_constant_
                 ise += e * e; iae += fabs(e); itae += t * fabs(e);
             }
             ++frames;
+            if (traced) trace_frame<M>(a.io, (size_t)b * T + k, w.Pd, w.X, dq_l, kappa,
+                                       so.flags | ib_flags | (so.epoch << UVS_FLAG_EPOCH_SHIFT), lane);
+            if (a.io.dq_in && lane < 6) dq_l = a.io.dq_in[((size_t)b * T + k) * 6 + lane];     // replay gate: recorded command
             if (lane < 6) {                                              // experiment.py:320,335
                 w.dq[lane] = dq_l;
                 double v = dq_l;

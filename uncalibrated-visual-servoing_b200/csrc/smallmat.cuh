@@ -83,159 +83,85 @@ UVS_DEV void chol_forward(const double (&L)[M * (M + 1) / 2], double (&x)[M]) {
     }
 }
 
-// Slow, rank-revealing fallback of the IBVS pseudo-inverse (one thread, rolled loops, local arrays):
-// x = pinv(J) b through the cyclic-Jacobi eigen-decomposition of the smaller Gram matrix, with
-// eigenvalues <= 64 eps lambda_max discarded.  J [MM x 6] row-major.  J == 0 gives x = 0, as
-// np.linalg.pinv does (experiment.py:312).
-static __device__ __noinline__ void pinv_fallback(int MM, const double* J, const double* b, double* x) {
-    const int K = MM >= 6 ? 6 : MM;
-    double A[6][6], V[6][6], rhs[6], y[6];
-    for (int i = 0; i < K; ++i)
-        for (int j = 0; j < K; ++j) {
-            double s = 0.0;
-            if (MM >= 6) for (int r = 0; r < MM; ++r) s += J[r * 6 + i] * J[r * 6 + j];
-            else for (int c = 0; c < 6; ++c) s += J[i * 6 + c] * J[j * 6 + c];
-            A[i][j] = s;
-            V[i][j] = (i == j) ? 1.0 : 0.0;
-        }
-    for (int i = 0; i < K; ++i) {
-        double s = 0.0;
-        if (MM >= 6) for (int r = 0; r < MM; ++r) s += J[r * 6 + i] * b[r];
-        else s = b[i];
-        rhs[i] = s;
-        y[i] = 0.0;
-    }
-    for (int sweep = 0; sweep < 30; ++sweep) {
-        double off = 0.0, diag = 0.0;
-        for (int i = 0; i < K; ++i) {
-            diag += A[i][i] * A[i][i];
-            for (int j = 0; j < i; ++j) off += A[i][j] * A[i][j];
-        }
-        if (!(off > 1e-40 * diag)) break;
-        for (int p = 0; p < K - 1; ++p)
-            for (int q = p + 1; q < K; ++q) {
-                const double apq = A[p][q];
-                if (apq == 0.0) continue;
-                const double theta = (A[q][q] - A[p][p]) / (2.0 * apq);
-                const double t = copysign(1.0, theta) / (fabs(theta) + sqrt(theta * theta + 1.0));
-                const double c = rsqrt(t * t + 1.0), sn = t * c;
-                for (int k = 0; k < K; ++k) {
-                    const double akp = A[k][p], akq = A[k][q];
-                    A[k][p] = c * akp - sn * akq;
-                    A[k][q] = sn * akp + c * akq;
-                }
-                for (int k = 0; k < K; ++k) {
-                    const double apk = A[p][k], aqk = A[q][k];
-                    A[p][k] = c * apk - sn * aqk;
-                    A[q][k] = sn * apk + c * aqk;
-                }
-                for (int k = 0; k < K; ++k) {
-                    const double vkp = V[k][p], vkq = V[k][q];
-                    V[k][p] = c * vkp - sn * vkq;
-                    V[k][q] = sn * vkp + c * vkq;
-                }
-            }
-    }
-    double lmax = 0.0;
-    for (int i = 0; i < K; ++i) lmax = fmax(lmax, A[i][i]);
-    const double cut = 64.0 * 2.220446049250313e-16 * lmax;
-    for (int e = 0; e < K; ++e) {
-        const double lam = A[e][e];
-        if (!(lam > cut) || !(lmax > 0.0)) continue;
-        double proj = 0.0;
-        for (int i = 0; i < K; ++i) proj += V[i][e] * rhs[i];
-        proj /= lam;
-        for (int i = 0; i < K; ++i) y[i] += V[i][e] * proj;
-    }
-    if (MM >= 6) {
-        for (int i = 0; i < 6; ++i) x[i] = y[i];
-    } else {
-        for (int c = 0; c < 6; ++c) {
-            double s = 0.0;
-            for (int r = 0; r < MM; ++r) s += J[r * 6 + c] * y[r];
-            x[c] = s;
-        }
-    }
-}
-
-// The same fallback for the 6 x 6 Gram case (MM >= 6), run by the GS lanes of a group together with both work matrices in
-// shared memory (`big`: 72 doubles, A then V) instead of one lane's local memory: the rotation sequence and every formula
-// are those of pinv_fallback (same results), but the three 6-long update loops of a rotation are one step of six lanes,
-// so it is ~4x faster — the 3-feature scene's square Jacobian passes near its singular configurations under impulsive
-// noise with KF / IMCC-KF and this path then runs on a sizeable share of the frames.  rhs = J^T b is read from `g`
-// (6 doubles, already computed by the fast path), the result goes to `x_out` (6 doubles, shared).  Every lane of the
-// group must call; `gl` = lane index inside the group.
+// Rank-revealing fallback of the IBVS pseudo-inverse: x = pinv(J) b with np.linalg.pinv's semantics
+// (experiment.py:312: SVD, singular values <= 1e-15 sigma_max discarded) by one-sided (Hestenes) Jacobi ON J ITSELF, run
+// cooperatively by the GS lanes of a group.  Working on J keeps the small singular values to high relative accuracy
+// down to the numpy cutoff; an eigen-decomposition of the Gram matrix (what this function replaced) squares the
+// condition number and cannot resolve sigma < ~1e-8 sigma_max, so it truncated where numpy still inverts.
+//   W = J (MM x 6) for MM >= 6, W = J^T (6 x MM) for MM < 6:  R rows, C <= 6 columns.  Plane rotations from the right
+//   orthogonalise the columns of A = W V (V accumulates them); at convergence A = U Sigma, so
+//   MM >= 6:  x = V Sigma^-2 A^T b            MM < 6:  x = A Sigma^-2 V^T b          (columns with sigma > cutoff only).
+// J: [MM x 6] row-major, b: MM doubles, both in shared memory; `work`: R*C + C*C doubles of per-group shared scratch
+// (84 for MM = 8); x_out: 6 doubles (shared).  Every lane of the group must call; gl = lane index inside the group.
+// J == 0 gives x = 0, as numpy does.  A rotation costs ~60 instructions per lane, a sweep C(C-1)/2 rotations, and the
+// cyclic sweeps stop when one of them rotated nothing (typically 5-8 sweeps); rare by construction (cond(J) >~ 3e6).
 template <int GS>
-static __device__ __noinline__ void pinv_fallback_coop(int MM, const double* J, const double* g, double* big, double* x_out,
-                                                       int gl) {
-    constexpr int K = 6;
-    static_assert(GS >= K, "one lane per row of the Gram matrix");
+static __device__ __noinline__ void pinv_fallback_osj(int MM, const double* J, const double* b, double* work,
+                                                      double* x_out, int gl) {
     const int lane = threadIdx.x & 31;
     const unsigned mask = (GS == 32) ? 0xffffffffu : (((1u << (GS & 31)) - 1u) << ((lane / GS) * GS));
-    double* A = big;
-    double* V = big + 36;
+    const bool tall = MM >= 6;
+    const int R = tall ? MM : 6, C = tall ? 6 : MM;
+    double* A = work;             // R x C, row-major (stride C)
+    double* V = work + R * C;     // C x C
     __syncwarp(mask);
-    for (int e = gl; e < 36; e += GS) {
-        const int i = e / 6, j = e % 6;
-        double acc = 0.0;
-        for (int r = 0; r < MM; ++r) acc += J[r * 6 + i] * J[r * 6 + j];
-        A[e] = acc;
-        V[e] = (i == j) ? 1.0 : 0.0;
+    for (int e = gl; e < R * C; e += GS) {
+        const int r = e / C, c = e % C;
+        A[e] = tall ? J[r * 6 + c] : J[c * 6 + r];
     }
+    for (int e = gl; e < C * C; e += GS) V[e] = (e / C == e % C) ? 1.0 : 0.0;
     __syncwarp(mask);
-    const int k = gl < K ? gl : K - 1;                 // lanes >= 6 shadow lane 5 and do not store
-    const bool own = gl < K;
-    for (int sweep = 0; sweep < 30; ++sweep) {
-        double off = 0.0, diag = 0.0;
-        for (int i = 0; i < K; ++i) {
-            diag += A[i * 6 + i] * A[i * 6 + i];
-            for (int j = 0; j < i; ++j) off += A[i * 6 + j] * A[i * 6 + j];
-        }
-        if (!(off > 1e-40 * diag)) break;              // uniform in the group: every lane read the same values
-        for (int p = 0; p < K - 1; ++p)
-            for (int q = p + 1; q < K; ++q) {
-                const double apq = A[p * 6 + q];
-                if (apq == 0.0) continue;              // uniform
-                const double theta = (A[q * 6 + q] - A[p * 6 + p]) / (2.0 * apq);
-                const double t = copysign(1.0, theta) / (fabs(theta) + sqrt(theta * theta + 1.0));
-                const double c = rsqrt(t * t + 1.0), sn = t * c;
-                // columns p, q of row k (A and V)
-                const double akp = A[k * 6 + p], akq = A[k * 6 + q];
-                const double vkp = V[k * 6 + p], vkq = V[k * 6 + q];
-                __syncwarp(mask);                       // all reads of this rotation's inputs are done
-                if (own) {
-                    A[k * 6 + p] = c * akp - sn * akq;
-                    A[k * 6 + q] = sn * akp + c * akq;
-                    V[k * 6 + p] = c * vkp - sn * vkq;
-                    V[k * 6 + q] = sn * vkp + c * vkq;
+    for (int sweep = 0; sweep < 40; ++sweep) {
+        bool rotated = false;
+        for (int p = 0; p < C - 1; ++p)
+            for (int q = p + 1; q < C; ++q) {
+                double alpha = 0.0, beta = 0.0, gamma = 0.0;          // every lane: the same values (uniform control flow)
+                for (int r = 0; r < R; ++r) {
+                    const double ap = A[r * C + p], aq = A[r * C + q];
+                    alpha += ap * ap; beta += aq * aq; gamma += ap * aq;
                 }
-                __syncwarp(mask);
-                // rows p, q, column k
-                const double apk = A[p * 6 + k], aqk = A[q * 6 + k];
-                __syncwarp(mask);
-                if (own) {
-                    A[p * 6 + k] = c * apk - sn * aqk;
-                    A[q * 6 + k] = sn * apk + c * aqk;
+                if (!(fabs(gamma) > 1.1102230246251565e-16 * sqrt(alpha * beta))) continue;   // also: NaN, zero columns
+                rotated = true;
+                const double zeta = (beta - alpha) / (2.0 * gamma);
+                const double t = copysign(1.0, zeta) / (fabs(zeta) + sqrt(zeta * zeta + 1.0));
+                const double c = rsqrt(t * t + 1.0), sn = t * c;
+                __syncwarp(mask);                                     // all lanes have read columns p, q
+                for (int i = gl; i < R + C; i += GS) {                // rows of A, then rows of V
+                    double* row = (i < R) ? A + i * C : V + (i - R) * C;
+                    const double vp = row[p], vq = row[q];
+                    row[p] = c * vp - sn * vq;
+                    row[q] = sn * vp + c * vq;
                 }
                 __syncwarp(mask);
             }
+        if (!rotated) break;
     }
-    double lmax = 0.0;
-    for (int i = 0; i < K; ++i) lmax = fmax(lmax, A[i * 6 + i]);
-    const double cut = 64.0 * 2.220446049250313e-16 * lmax;
+    // squared singular values, cutoff (numpy: s > rcond * s_max with rcond = 1e-15), projections
+    double s2[6], smax2 = 0.0;
+    for (int c = 0; c < C; ++c) {
+        double a = 0.0;
+        for (int r = 0; r < R; ++r) a += A[r * C + c] * A[r * C + c];
+        s2[c] = a;
+        smax2 = fmax(smax2, a);
+    }
+    const int i = gl < 6 ? gl : 5;
     double y = 0.0;
-    for (int e = 0; e < K; ++e) {
-        const double lam = A[e * 6 + e];
-        if (!(lam > cut) || !(lmax > 0.0)) continue;
+    for (int c = 0; c < C; ++c) {
+        if (!(sqrt(s2[c]) > 1e-15 * sqrt(smax2)) || !(smax2 > 0.0)) continue;
         double proj = 0.0;
-        for (int i = 0; i < K; ++i) proj += V[i * 6 + e] * g[i];
-        proj /= lam;
-        y += V[k * 6 + e] * proj;
+        if (tall) { for (int r = 0; r < R; ++r) proj += A[r * C + c] * b[r]; }
+        else      { for (int k = 0; k < C; ++k) proj += V[k * C + c] * b[k]; }
+        proj /= s2[c];
+        y += (tall ? V[i * C + c] : A[i * C + c]) * proj;
     }
     __syncwarp(mask);
-    if (own) x_out[k] = y;
+    if (gl < 6) x_out[gl] = y;
     __syncwarp(mask);
 }
+
+// doubles of per-group shared scratch pinv_fallback_osj needs for an M x 6 Jacobian with M >= 6 (M < 6 fits the group's
+// own `sc` block)
+__host__ __device__ constexpr int pinv_scratch_doubles(int M) { return (M >= 6) ? M * 6 + 36 : 0; }
 
 // Cooperative minimum-norm least squares x = pinv(J) b  (experiment.py:312) by a group of GS lanes
 // (GS = 32: one problem per warp; GS = 8 or 2: several problems per warp, the block-diagonal family).
@@ -243,9 +169,9 @@ static __device__ __noinline__ void pinv_fallback_coop(int MM, const double* J, 
 // per-group shared scratch; gl = lane index inside the group.  All 32 lanes of the warp must call.
 // Fast path: Cholesky of the smaller Gram matrix (J^T J for M >= 6, J J^T for M < 6) + one step of
 // iterative refinement on the residual (corrected semi-normal equations, error ~ eps cond(J)); if a
-// Cholesky pivot is <= 1e-13 trace(Gram) (cond(J) >~ 3e6) group lane 0 runs pinv_fallback.
-// Result in x on every lane of the group.  big: optional 72 doubles of per-group shared scratch; when given (and
-// M >= 6) the fallback runs cooperatively (pinv_fallback_coop) instead of on group lane 0.
+// Cholesky pivot is <= 1e-13 trace(Gram) (cond(J) >~ 3e6) the group runs pinv_fallback_osj (one-sided Jacobi on J,
+// numpy's 1e-15 sigma_max cutoff).  Result in x on every lane of the group.  big: pinv_scratch_doubles(M) doubles of
+// per-group shared scratch, required for M >= 6 (M < 6 uses the free head of `sc`).
 template <int M, int GS>
 UVS_DEV void pinv_group(const double* J, double b_lane, double* sc, int gl, double (&x)[6], int& flags,
                         double* big = nullptr) {
@@ -360,8 +286,7 @@ UVS_DEV void pinv_group(const double* J, double b_lane, double* sc, int gl, doub
     __syncwarp();
     if (!ok) {
         flags |= UVS_FLAG_RANK_DEFICIENT;
-        if (M >= 6 && GS >= 6 && big != nullptr) pinv_fallback_coop<(GS >= 6 ? GS : 32)>(M, J, sg, big, sx, gl);
-        else if (gl == 0) pinv_fallback(M, J, sb, sx);
+        pinv_fallback_osj<GS>(M, J, sb, (M >= 6) ? big : sG, sx, gl);      // M < 6: sG (21 doubles) is unused, A + V need 6 M + M^2
     }
     __syncwarp();
     if (!ok) {

@@ -28,6 +28,8 @@ struct TwistArgs {
 struct alignas(16) TwistWS {
     double Jg[36];          // geometric Jacobian, row-major (rows v;w, columns joints)
     double jac[72];         // work matrices of the cooperative pseudo-inverse fallback (wrist singularities)
+    double R[9];            // camera rotation R06 used by the control law (the start pose's when tw.stale_fk)
+    double pad;
 };
 
 template <int M, bool MCKF>
@@ -154,6 +156,7 @@ __global__ void __launch_bounds__(kTwistThreads, 2) twist_closed_loop_kernel(con
         double err2 = (double)M;                                           // error = ones(m)  (kalman_4_features.py:70)
         const bool servo = (cfg.v_max > 0.0) || (cfg.a_max > 0.0) || (cfg.servo_gain > 0.0 && cfg.servo_gain != 1.0);
         double v_prev[6] = {0, 0, 0, 0, 0, 0};
+        const bool traced = io_traced(a.io);
 
         for (int k = 0; k < T; ++k) {
             if (tw.err_threshold >= 0.0 && !(sqrt(err2) > tw.err_threshold)) break;     // kalman_4_features.py:111
@@ -178,7 +181,11 @@ __global__ void __launch_bounds__(kTwistThreads, 2) twist_closed_loop_kernel(con
                 }
                 ur10_chain_columns(sn, cs, lane, T6, zax, org);
             }
-            if (lane < 6) {                                                // ur10_simulation.py:117-139
+            // tw.stale_fk: the scripts that never refresh UR10Simulation's cached transforms inside the loop keep the
+            // start pose's J_geom and R06 (kalman_4_features.py:165-169; frame 0 is at the start pose)
+            const bool refresh_fk = !tw.stale_fk || k == 0;
+            if (refresh_fk && lane < 9) ts.R[lane] = T6.r[lane / 3][lane % 3];
+            if (refresh_fk && lane < 6) {                                  // ur10_simulation.py:117-139
                 const double dx = T6.p[0] - org[0], dy = T6.p[1] - org[1], dz = T6.p[2] - org[2];
                 ts.Jg[0 * 6 + lane] = zax[1] * dz - zax[2] * dy;
                 ts.Jg[1 * 6 + lane] = zax[2] * dx - zax[0] * dz;
@@ -209,6 +216,7 @@ __global__ void __launch_bounds__(kTwistThreads, 2) twist_closed_loop_kernel(con
             double kappa = 1.0;
             constexpr bool DEFER = FAST && M >= 6 && !MCKF && !ANALYTIC;
             bool rank_pending = false;
+            int step_flags = 0;
             if constexpr (ANALYTIC) {
                 const double f_p = shfl_d(f_l, lane ^ 1);
                 if (lane < M) {
@@ -225,7 +233,9 @@ __global__ void __launch_bounds__(kTwistThreads, 2) twist_closed_loop_kernel(con
                 StepOut so;
                 kappa = dense_step<M, FILTER, DEFER, FAST>(pb, w, cc, cfg.filt, h, z, sigma, lane, so, 1.0 / (sigma * sigma));
                 flags_all |= so.flags;
+                step_flags = so.flags | (so.epoch << UVS_FLAG_EPOCH_SHIFT);
                 rank_pending = so.rank_pending;
+                if (so.flags & kAbortFlags) { status = UVS_STATUS_FAIL; break; }  // common.cuh: kAbortFlags
             }
 
             // ---- control: dp = -GAIN pinv(J) e ; dx = kron(I2, R^T) dp ; dq = pinv(J_geom) dx ----
@@ -244,14 +254,16 @@ __global__ void __launch_bounds__(kTwistThreads, 2) twist_closed_loop_kernel(con
             double dx_l = 0.0;
 #pragma unroll
             for (int c = 0; c < 3; ++c) {
-                const double lin = T6.r[0][c] * dp[0] + T6.r[1][c] * dp[1] + T6.r[2][c] * dp[2];
-                const double ang = T6.r[0][c] * dp[3] + T6.r[1][c] * dp[4] + T6.r[2][c] * dp[5];
+                const double r0 = ts.R[c], r1 = ts.R[3 + c], r2 = ts.R[6 + c];
+                const double lin = r0 * dp[0] + r1 * dp[1] + r2 * dp[2];
+                const double ang = r0 * dp[3] + r1 * dp[4] + r2 * dp[5];
                 dx_l = (lane == c) ? lin : ((lane == 3 + c) ? ang : dx_l);
             }
             double dq[6];
             int jg_flags = 0;
             pinv_warp<6>(ts.Jg, dx_l, w.ib, lane, dq, jg_flags, ts.jac);
             flags_all |= ib_flags | jg_flags;
+            const int frame_flags = step_flags | ib_flags | jg_flags;
 
             bool bad = false;
 #pragma unroll
@@ -278,6 +290,12 @@ __global__ void __launch_bounds__(kTwistThreads, 2) twist_closed_loop_kernel(con
             for (int o = 16; o > 0; o >>= 1) e2 += shfl_xor_d(e2, o);
             err2 = e2;
             ++frames;
+            if (traced) {                                                  // per-frame trace (uvs_closed_loop_io, ABI 4)
+                double dq_l = dq[0];
+#pragma unroll
+                for (int r = 1; r < 6; ++r) dq_l = (lane == r) ? dq[r] : dq_l;
+                trace_frame<M>(a.io, (size_t)b * T + k, w.Pd, w.X, dq_l, kappa, frame_flags, lane);
+            }
 #pragma unroll
             for (int r = 0; r < 6; ++r) {
                 if (lane == r) w.dq[r] = dp[r];

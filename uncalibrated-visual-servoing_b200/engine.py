@@ -195,66 +195,72 @@ def closed_loop_cfg(filt, noise, *, T, dt, ibvs_gain, q_start, desired_f, target
     return cfg
 
 
-def closed_loop(cfg, trial0, B, *, want_log=False, want_state=False, p_layout=L.P_BLOCKS, noise_in=None, q0_in=None,
-                X0_in=None, device="cuda", out=None):
-    """Runs B closed-loop trials; returns a dict of CUDA tensors (no host sync)."""
-    _require_cuda()
+def _loop_outputs(cfg, B, want_log, want_state, want_trace, p_layout, device):
     m = 2 * cfg.filt.nf
     N = 6 * m
-    if out is None:
-        out = dict(stats=torch.empty((B, 3), dtype=torch.float64, device=device),
-                   status=torch.empty((B,), dtype=torch.int32, device=device),
-                   frames=torch.empty((B,), dtype=torch.int32, device=device),
-                   flags=torch.empty((B,), dtype=torch.int32, device=device))
-        if want_log:
-            out["log"] = torch.zeros((B, cfg.T, 6 + 2 * m), dtype=torch.float64, device=device)
-        if want_state:
-            out["X"] = torch.empty((B, N), dtype=torch.float64, device=device)
-            shape = (B, N, N) if p_layout == L.P_DENSE else (B, m, 6, 6)
-            out["P"] = torch.zeros(shape, dtype=torch.float64, device=device)
+    out = dict(stats=torch.empty((B, 3), dtype=torch.float64, device=device),
+               status=torch.empty((B,), dtype=torch.int32, device=device),
+               frames=torch.empty((B,), dtype=torch.int32, device=device),
+               flags=torch.empty((B,), dtype=torch.int32, device=device))
+    if want_log:
+        out["log"] = torch.zeros((B, cfg.T, 6 + 2 * m), dtype=torch.float64, device=device)
+    pshape = (N, N) if p_layout == L.P_DENSE else (m, 6, 6)
+    if want_state:
+        out["X"] = torch.empty((B, N), dtype=torch.float64, device=device)
+        out["P"] = torch.zeros((B,) + pshape, dtype=torch.float64, device=device)
+    if want_trace:          # per-frame trace (uvs_closed_loop_io, ABI 4); frames a trial did not run stay zero
+        out["X_log"] = torch.zeros((B, cfg.T, N), dtype=torch.float64, device=device)
+        out["P_log"] = torch.zeros((B, cfg.T, m, 6, 6), dtype=torch.float64, device=device)     # diagonal blocks
+        out["dq_log"] = torch.zeros((B, cfg.T, 6), dtype=torch.float64, device=device)
+        out["kappa_log"] = torch.zeros((B, cfg.T, m), dtype=torch.float64, device=device)
+        out["flags_log"] = torch.zeros((B, cfg.T), dtype=torch.int32, device=device)
+    return out
+
+
+def _loop_io(out, p_layout, noise_in, q0_in, X0_in, dq_in):
     io = L.ClosedLoopIO()
     io.stats, io.status = _ptr(out["stats"]).value, _ptr(out["status"]).value
     io.frames, io.flags = _ptr(out.get("frames")).value, _ptr(out.get("flags")).value
     io.log, io.X_out, io.P_out = _ptr(out.get("log")).value, _ptr(out.get("X")).value, _ptr(out.get("P")).value
     io.noise_in, io.q0_in, io.X0_in = _ptr(noise_in).value, _ptr(q0_in).value, _ptr(X0_in).value
     io.p_layout = int(p_layout)
+    io.dq_in = _ptr(dq_in).value
+    io.X_log, io.P_log, io.dq_log = _ptr(out.get("X_log")).value, _ptr(out.get("P_log")).value, _ptr(out.get("dq_log")).value
+    io.kappa_log, io.flags_log = _ptr(out.get("kappa_log")).value, _ptr(out.get("flags_log")).value
+    return io
+
+
+def closed_loop(cfg, trial0, B, *, want_log=False, want_state=False, want_trace=False, p_layout=L.P_BLOCKS,
+                noise_in=None, q0_in=None, X0_in=None, dq_in=None, device="cuda", out=None):
+    """Runs B closed-loop trials; returns a dict of CUDA tensors (no host sync).  ``want_trace`` adds the per-frame
+    X / P / dq / kappa / flags logs; ``dq_in`` [B,T,6] replays a recorded command stream (the replay gate of the
+    closed-loop kernels, include/uvs_b200.h)."""
+    _require_cuda()
+    if out is None:
+        out = _loop_outputs(cfg, B, want_log, want_state, want_trace, p_layout, device)
+    io = _loop_io(out, p_layout, noise_in, q0_in, X0_in, dq_in)
     L.check(L.load().uvs_closed_loop(C.byref(cfg), int(trial0), int(B), C.byref(io), _stream()), "uvs_closed_loop")
     return out
 
 
 def twist_cfg(*, x0_mode=L.X0_IMAGE_JACOBIAN, depth_mode=L.DEPTH_DISTANCE, dp_zero_mask=0, focal_x0=1024.0,
-              focal=200.91975387103875, err_threshold=-1.0):
+              focal=200.91975387103875, err_threshold=-1.0, stale_fk=False):
     """The parameters only the reference's tests/ scripts have (include/uvs_b200.h: uvs_twist_cfg)."""
     tw = L.TwistCfg()
     tw.x0_mode, tw.depth_mode, tw.dp_zero_mask = int(x0_mode), int(depth_mode), int(dp_zero_mask)
+    tw.stale_fk = int(bool(stale_fk))
     tw.focal_x0, tw.focal, tw.err_threshold = float(focal_x0), float(focal), float(err_threshold)
     return tw
 
 
-def twist_loop(cfg, tw, trial0, B, *, want_log=False, want_state=False, p_layout=L.P_DENSE, noise_in=None,
-               q0_in=None, X0_in=None, device="cuda", out=None):
+def twist_loop(cfg, tw, trial0, B, *, want_log=False, want_state=False, want_trace=False, p_layout=L.P_DENSE,
+               noise_in=None, q0_in=None, X0_in=None, device="cuda", out=None):
     """B trials of the tests/-style camera-twist loop (tests/{ibvs,kalman,mckf}_*.py); same outputs as
     ``closed_loop``.  cfg.ibvs_gain is the scripts' GAIN, cfg.dt their TS."""
     _require_cuda()
-    m = 2 * cfg.filt.nf
-    N = 6 * m
     if out is None:
-        out = dict(stats=torch.empty((B, 3), dtype=torch.float64, device=device),
-                   status=torch.empty((B,), dtype=torch.int32, device=device),
-                   frames=torch.empty((B,), dtype=torch.int32, device=device),
-                   flags=torch.empty((B,), dtype=torch.int32, device=device))
-        if want_log:
-            out["log"] = torch.zeros((B, cfg.T, 6 + 2 * m), dtype=torch.float64, device=device)
-        if want_state:
-            out["X"] = torch.empty((B, N), dtype=torch.float64, device=device)
-            shape = (B, N, N) if p_layout == L.P_DENSE else (B, m, 6, 6)
-            out["P"] = torch.zeros(shape, dtype=torch.float64, device=device)
-    io = L.ClosedLoopIO()
-    io.stats, io.status = _ptr(out["stats"]).value, _ptr(out["status"]).value
-    io.frames, io.flags = _ptr(out.get("frames")).value, _ptr(out.get("flags")).value
-    io.log, io.X_out, io.P_out = _ptr(out.get("log")).value, _ptr(out.get("X")).value, _ptr(out.get("P")).value
-    io.noise_in, io.q0_in, io.X0_in = _ptr(noise_in).value, _ptr(q0_in).value, _ptr(X0_in).value
-    io.p_layout = int(p_layout)
+        out = _loop_outputs(cfg, B, want_log, want_state, want_trace, p_layout, device)
+    io = _loop_io(out, p_layout, noise_in, q0_in, X0_in, None)
     L.check(L.load().uvs_twist_loop(C.byref(cfg), C.byref(tw), int(trial0), int(B), C.byref(io), _stream()),
             "uvs_twist_loop")
     return out
