@@ -4,12 +4,16 @@
     python bench.py --impl reference --steps 1 --warmup 0          # reference algorithm on host cores
     torchrun --nproc-per-node N bench.py --gpus N ...              # one rank per GPU
 
-Workload (BASELINE.json configs[2]): RMCKF (= Method.GMCKF), 4 features (48 states), closed-loop
-kinematic UR10 IBVS, impulsive alpha-stable noise swept over alpha = linspace(1, 2, 12) with
-annealing, T = 300 frames, 100 000 trials per GPU.  One "step" = one pass of the hot path over one
-batch = one kernel launch that runs every trial of the batch through all T frames (+ the
-per-level statistics reduction, + the NCCL all-reduce of those sums when N > 1).  A filter-step
-is one frame of one trial; only frames actually executed are counted.
+Workload: RMCKF (= Method.GMCKF), 4 features (48 states), closed-loop kinematic UR10 IBVS, impulsive
+alpha-stable noise swept over alpha = linspace(1, 2, 12) with annealing, T = 300 frames.
+  N = 1: BASELINE.json configs[2], 100 000 trials per step.
+  N > 1: BASELINE.json configs[3], 1 000 000 trials per step sharded over the ranks (contiguous trial
+         ranges, sweep.shard_range; strong scaling), unless --trials asks for a fixed count per GPU.
+One "step" = one pass of the hot path over one batch = one kernel launch that runs every trial of the
+shard through all T frames + the per-level statistics reduction into a device-resident block.  There is
+no collective and no host synchronisation inside the step loop: the per-level sums of all steps are
+all-reduced ONCE, packed, after the last step (inside the timed region).  A filter-step is one frame of
+one trial; only frames actually executed are counted.
 
 Prints ONE JSON line (rank 0).  `value` is timed with CUDA events with everything resident on
 the device; `e2e` goes through the host-buffer C-ABI entry point (uvs_closed_loop_host:
@@ -61,25 +65,40 @@ def parse():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--mode", default="dense", choices=["dense", "blockdiag"])
-    ap.add_argument("--trials", type=int, default=100_000, help="trials per GPU per step")
+    ap.add_argument("--trials", type=int, default=None, help="trials per GPU per step (weak scaling; default at N = 1: 100 000)")
+    ap.add_argument("--total-trials", type=int, default=None,
+                    help="trials of the whole job per step, sharded over the ranks (strong scaling; default at N > 1: "
+                         "1 000 000 = BASELINE configs[3])")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-blockdiag-extra", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip the trajectory-logging and camera-twist legs")
     return ap.parse_args()
 
 
-def workload_name(mode, trials):
+def workload_name(mode, trials, total=None, world=1):
+    size = (f"{total} trials per step sharded over {world} GPUs (BASELINE configs[3])" if total is not None and world > 1
+            else f"{trials} trials per GPU per step (BASELINE configs[2])")
     return (f"RMCKF(GMCKF) 4 features / 48 states, closed-loop kinematic UR10 IBVS, alpha-stable noise "
-            f"alpha=linspace(1,2,12) beta=0 gamma=1, annealing, kernel_bw=10, T=300 frames, "
-            f"{trials} trials per GPU per step (BASELINE configs[2]), covariance={mode}")
+            f"alpha=linspace(1,2,12) beta=0 gamma=1, annealing, kernel_bw=10, T=300 frames, {size}, covariance={mode}")
+
+
+def plan(a, rank, world):
+    """(trials of this rank, first global trial, total trials, scaling) — sweep.shard_range for the strong case."""
+    if a.trials is None and (world > 1 or a.total_trials is not None):
+        total = a.total_trials or 1_000_000
+        base, extra = divmod(total, world)
+        lo = rank * base + min(rank, extra)
+        return base + (1 if rank < extra else 0), lo, total, "strong"
+    B = a.trials or 100_000
+    return B, rank * B, world * B, "weak"
 
 
 # ------------------------------------------------------------------------- CPU arm (oracle port)
 def _cpu_worker(args):
     os.environ["OMP_NUM_THREADS"] = os.environ["OPENBLAS_NUM_THREADS"] = os.environ["MKL_NUM_THREADS"] = "1"
-    trial0, n = args
-    from oracle import closed_loop as CL
-    cfg = CL.make_cfg(annealing=True, noise_seed=NOISE_SEED, pose_seed=POSE_SEED)
+    trial0, n, method = args
+    from oracle import closed_loop as CL, filters as F
+    cfg = CL.make_cfg(method=getattr(F, method), annealing=True, noise_seed=NOISE_SEED, pose_seed=POSE_SEED)
     frames = 0
     t0 = time.perf_counter()
     for t in range(trial0, trial0 + n):
@@ -89,14 +108,14 @@ def _cpu_worker(args):
     return frames, time.perf_counter() - t0
 
 
-def cpu_sample(trials_per_core, cores=None, trial0=0):
+def cpu_sample(trials_per_core, cores=None, trial0=0, method="GMCKF"):
     """The oracle's as-written NumPy closed loop (experiment.py restated, dense) on all host cores,
     one single-threaded process per core.  Returns (filter-steps/s aggregate, cores, frames, seconds)."""
     cores = cores or os.cpu_count() or 1
     os.environ.setdefault("OMP_NUM_THREADS", "1")
     os.environ.setdefault("OPENBLAS_NUM_THREADS", "1")
     ctx = mp.get_context("spawn")
-    jobs = [(trial0 + i * trials_per_core, trials_per_core) for i in range(cores)]
+    jobs = [(trial0 + i * trials_per_core, trials_per_core, method) for i in range(cores)]
     t0 = time.perf_counter()
     with ctx.Pool(cores) as pool:
         res = pool.map(_cpu_worker, jobs)
@@ -104,6 +123,47 @@ def cpu_sample(trials_per_core, cores=None, trial0=0):
     work = max(r[1] for r in res)               # slowest worker = the parallel region without pool start-up
     frames = sum(r[0] for r in res)
     return frames / work, cores, frames, wall
+
+
+def reference_calibration():
+    """port / reference ratios measured in the build container (tools/cpu_reference.py -> profiles/cpu_reference.json):
+    the unmodified /root/reference Experiment.run() + kinematic fake robot against the oracle port this file times.
+    The reference tree does not exist on the GPU box, so the ratio travels as a committed calibration."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "cpu_reference.json")) as fh:
+            return json.load(fh)
+    except (OSError, ValueError):
+        return None
+
+
+def cpu_baseline_block(cores=None, reps=3):
+    """the port on all host cores, per estimator, best of `reps` bounded samples, with the
+    committed port / reference calibration beside it."""
+    cal = reference_calibration()
+    per = {}
+    wall = 0.0
+    for method, tpc in (("GMCKF", 60), ("KF", 40), ("MCKF", 24)):
+        best = 0.0
+        for r in range(reps if method == "GMCKF" else 2):
+            v, cores, frames, w = cpu_sample(tpc, cores, trial0=500 * r, method=method)
+            best = max(best, v)
+            wall += w
+        per[method] = best
+    block = {"value": per["GMCKF"], "unit": UNIT, "cores": cores, "kind": "port",
+             "per_estimator": {("RMCKF(GMCKF)" if k == "GMCKF" else k): v for k, v in per.items()},
+             "sample": f"{cores} single-threaded processes x (60 RMCKF / 40 KF / 24 MCKF) closed-loop trials x {T_FRAMES} "
+                       f"frames per repetition, best of {reps} (RMCKF) / 2; oracle as-written NumPy restatement of "
+                       f"experiment.py; {wall:.0f} s wall in total"}
+    if cal:
+        bm = cal["by_method"]
+        block["port_over_reference"] = bm["GMCKF"]["port_over_reference_allcores"]
+        block["port_over_reference_per_estimator"] = {k: v["port_over_reference_allcores"] for k, v in bm.items()}
+        block["reference_equivalent"] = per["GMCKF"] / bm["GMCKF"]["port_over_reference_allcores"]
+        block["calibration"] = ("port / reference measured in the build container by tools/cpu_reference.py "
+                                f"(profiles/r02_cpu_reference.md: unmodified Experiment.run() + kinematic fake robot, "
+                                f"{cal['meta']['cores']} cores, best of {cal['meta']['reps']}); the reference tree cannot "
+                                "travel to the GPU box")
+    return block
 
 
 def run_reference(a):
@@ -120,15 +180,20 @@ def run_reference(a):
         vals.append(v)
         ms.append(1e3 * frames / v)
     value = float(np.mean(vals))
+    cal = reference_calibration()
     sample = f"{cores} processes x {tpc} closed-loop trials x {T_FRAMES} frames per step (as-written NumPy restatement, OMP_NUM_THREADS=1)"
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": a.gpus, "steps": max(1, a.steps),
-        "warmup": a.warmup, "ms_per_step": float(np.mean(ms)), "higher_is_better": True, "scaling": "weak",
+        "warmup": a.warmup, "ms_per_step": float(np.mean(ms)), "higher_is_better": True, "scaling": plan(a, 0, a.gpus)[3],
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": workload_name("dense", a.trials), "trials_per_gpu": a.trials, "frames": T_FRAMES,
+        "config": {"workload": workload_name("dense", plan(a, 0, a.gpus)[0], plan(a, 0, a.gpus)[2], a.gpus),
+                   "trials_per_gpu": plan(a, 0, a.gpus)[0], "frames": T_FRAMES,
                    "sample": f"each step runs {cores * tpc} trials of that workload (bounded CPU sample)",
                    "noise_seed": NOISE_SEED, "pose_seed": POSE_SEED},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "cpu_baseline": dict({"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+                             **({"port_over_reference": cal["by_method"]["GMCKF"]["port_over_reference_allcores"],
+                                 "reference_equivalent": value / cal["by_method"]["GMCKF"]["port_over_reference_allcores"]}
+                                if cal else {})),
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }

@@ -59,10 +59,9 @@ enum { UVS_P_DENSE = 0,         /* [B, N, N]                                    
 #define UVS_FLAG_SKIP_MAXEPOCH   2   /* MCKF: fpi_epoch_max reached -> correction skipped (experiment.py:246-248) */
 #define UVS_FLAG_CX_SINGULAR     4   /* MCKF: a state weight underflowed (the reference raises out of run() at experiment.py:224);
                                         closed loops: the trial ends UVS_STATUS_FAIL on that frame */
-#define UVS_FLAG_NOT_SPD         8   /* Cholesky of P or S met a non-positive pivot (P0, Q, R must be SPD, so this means non-finite
-                                        arithmetic): correction skipped; closed loops: the trial ends UVS_STATUS_FAIL on that frame,
-                                        as the reference does through np.linalg.pinv raising on the NaN state (experiment.py:312-316) */
-#define UVS_FLAG_RANK_DEFICIENT 16   /* IBVS: Jacobian numerically rank deficient, eigen fallback used */
+#define UVS_FLAG_NOT_SPD         8   /* Cholesky of P or S met a non-positive pivot -> correction skipped, the trial goes on (the
+                                        reference inverts S without a Cholesky; P0, Q, R must be SPD) */
+#define UVS_FLAG_RANK_DEFICIENT 16   /* IBVS: cond(J) >~ 1e5, pseudo-inverse by one-sided Jacobi on J with numpy's 1e-15 sigma_max cutoff */
 #define UVS_FLAG_NONFINITE      32   /* trial failed: non-finite state / command (experiment.py:312-316) */
 #define UVS_FLAG_OUT_OF_VIEW    64   /* trial failed: a feature left the field of view (utils.py:73-78 -> NaN centroid) */
 #define UVS_FLAG_EPOCH_SHIFT     8

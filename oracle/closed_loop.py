@@ -62,7 +62,7 @@ def run_trial(cfg, trial, noise=None, q0=None, x0=None, record=False, dq_in=None
 
     A frame on which the reference raises out of Experiment.run() — np.linalg.inv(Cx) with a zero weight
     (experiment.py:224), np.linalg.cholesky(P) (:203), a singular innovation covariance outside GMCKF's try
-    block (:192, :238, :264) — ends the trial with FAIL, as the CUDA kernels do (csrc/common.cuh abort_flags).
+    block (:192, :238, :264) — ends the trial with FAIL (the CUDA kernels: csrc/common.cuh kAbortFlags).
     """
     nf = cfg["nf"]
     m, N = 2 * nf, 12 * nf

@@ -353,7 +353,7 @@ UVS_DEV void ibvs_with_rank_update(PBlock& pb, double* Pd, const double* Kt, con
 #pragma unroll
         for (int j = 0; j < K; ++j) {
             const double inv = L[tri(j, j)];
-            ok = ok && (inv * inv * gsum * 1e-13 < 1.0);
+            ok = ok && (inv * inv * gsum * kPinvPivotTol < 1.0);
         }
         chol_solve<K>(L, g);
         const int row = lane < M ? lane : M - 1;

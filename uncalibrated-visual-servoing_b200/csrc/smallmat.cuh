@@ -8,6 +8,9 @@
 
 namespace uvs {
 
+// hand-over from the Cholesky path of the pseudo-inverse to the rank-revealing one: pivot <= kPinvPivotTol * trace(Gram)
+constexpr double kPinvPivotTol = 1e-10;
+
 // packed lower-triangular index
 __host__ __device__ constexpr int tri(int i, int j) { return i * (i + 1) / 2 + j; }
 
@@ -94,7 +97,7 @@ UVS_DEV void chol_forward(const double (&L)[M * (M + 1) / 2], double (&x)[M]) {
 // J: [MM x 6] row-major, b: MM doubles, both in shared memory; `work`: R*C + C*C doubles of per-group shared scratch
 // (84 for MM = 8); x_out: 6 doubles (shared).  Every lane of the group must call; gl = lane index inside the group.
 // J == 0 gives x = 0, as numpy does.  A rotation costs ~60 instructions per lane, a sweep C(C-1)/2 rotations, and the
-// cyclic sweeps stop when one of them rotated nothing (typically 5-8 sweeps); rare by construction (cond(J) >~ 3e6).
+// cyclic sweeps stop when one of them rotated nothing (typically 5-8 sweeps); rare by construction (cond(J) >~ 1e5).
 template <int GS>
 static __device__ __noinline__ void pinv_fallback_osj(int MM, const double* J, const double* b, double* work,
                                                       double* x_out, int gl) {
@@ -136,26 +139,35 @@ static __device__ __noinline__ void pinv_fallback_osj(int MM, const double* J, c
             }
         if (!rotated) break;
     }
-    // squared singular values, cutoff (numpy: s > rcond * s_max with rcond = 1e-15), projections
+    // squared singular values, cutoff (numpy: s > rcond * s_max with rcond = 1e-15), projections.  Constant trip counts
+    // with a predicate keep s2 / proj in registers (statically indexed).
     double s2[6], smax2 = 0.0;
-    for (int c = 0; c < C; ++c) {
+#pragma unroll
+    for (int c = 0; c < 6; ++c) {
         double a = 0.0;
-        for (int r = 0; r < R; ++r) a += A[r * C + c] * A[r * C + c];
+        if (c < C) for (int r = 0; r < R; ++r) a += A[r * C + c] * A[r * C + c];
         s2[c] = a;
         smax2 = fmax(smax2, a);
     }
-    const int i = gl < 6 ? gl : 5;
-    double y = 0.0;
-    for (int c = 0; c < C; ++c) {
-        if (!(sqrt(s2[c]) > 1e-15 * sqrt(smax2)) || !(smax2 > 0.0)) continue;
-        double proj = 0.0;
-        if (tall) { for (int r = 0; r < R; ++r) proj += A[r * C + c] * b[r]; }
-        else      { for (int k = 0; k < C; ++k) proj += V[k * C + c] * b[k]; }
-        proj /= s2[c];
-        y += (tall ? V[i * C + c] : A[i * C + c]) * proj;
+    double proj[6];
+#pragma unroll
+    for (int c = 0; c < 6; ++c) {
+        double t = 0.0;
+        if (c < C && sqrt(s2[c]) > 1e-15 * sqrt(smax2) && smax2 > 0.0) {
+            if (tall) { for (int r = 0; r < R; ++r) t += A[r * C + c] * b[r]; }
+            else      { for (int k = 0; k < C; ++k) t += V[k * C + c] * b[k]; }
+            t /= s2[c];
+        }
+        proj[c] = t;
     }
     __syncwarp(mask);
-    if (gl < 6) x_out[gl] = y;
+    for (int i = gl; i < 6; i += GS) {                    // groups narrower than 6 lanes (GS = 2) take several components
+        double y = 0.0;
+#pragma unroll
+        for (int c = 0; c < 6; ++c)
+            if (c < C) y += (tall ? V[i * C + c] : A[i * C + c]) * proj[c];
+        x_out[i] = y;
+    }
     __syncwarp(mask);
 }
 
@@ -169,8 +181,9 @@ __host__ __device__ constexpr int pinv_scratch_doubles(int M) { return (M >= 6) 
 // per-group shared scratch; gl = lane index inside the group.  All 32 lanes of the warp must call.
 // Fast path: Cholesky of the smaller Gram matrix (J^T J for M >= 6, J J^T for M < 6) + one step of
 // iterative refinement on the residual (corrected semi-normal equations, error ~ eps cond(J)); if a
-// Cholesky pivot is <= 1e-13 trace(Gram) (cond(J) >~ 3e6) the group runs pinv_fallback_osj (one-sided Jacobi on J,
-// numpy's 1e-15 sigma_max cutoff).  Result in x on every lane of the group.  big: pinv_scratch_doubles(M) doubles of
+// Cholesky pivot is <= 1e-10 trace(Gram) (cond(J) >~ 1e5; the refined normal equations are good to ~(eps cond^2)^2, i.e.
+// 1e-11 there and 2e-6 at cond = 1e7, measured) the group runs pinv_fallback_osj (one-sided Jacobi on J, numpy's 1e-15
+// sigma_max cutoff, error ~ eps cond).  Result in x on every lane of the group.  big: pinv_scratch_doubles(M) doubles of
 // per-group shared scratch, required for M >= 6 (M < 6 uses the free head of `sc`).
 template <int M, int GS>
 UVS_DEV void pinv_group(const double* J, double b_lane, double* sc, int gl, double (&x)[6], int& flags,
@@ -225,7 +238,7 @@ UVS_DEV void pinv_group(const double* J, double b_lane, double* sc, int gl, doub
 #pragma unroll
     for (int j = 0; j < K; ++j) {
         const double inv = L[tri(j, j)];
-        ok = ok && (inv * inv * gmax * 1e-13 < 1.0);
+        ok = ok && (inv * inv * gmax * kPinvPivotTol < 1.0);
     }
     // the fast path runs unconditionally (it only touches registers and this group's scratch) so
     // that the warp-wide barriers below are reached by every lane whatever the other groups do

@@ -297,12 +297,16 @@ def closed_loop_host(cfg, trial0, B, pinned=True):
     return stats, status, frames
 
 
-def reduce_stats(stats, status, trial0, sweep_epoch, n_levels):
-    """Per-level sums [n_levels,3,3] = {n_ok, sum, sum of squares} and n_fail [n_levels]."""
+def reduce_stats(stats, status, trial0, sweep_epoch, n_levels, out=None):
+    """Per-level sums [n_levels,3,3] = {n_ok, sum, sum of squares} and n_fail [n_levels].  ``out`` = (sums, n_fail)
+    to ACCUMULATE into existing buffers (e.g. two views of one packed tensor that is all-reduced once)."""
     _require_cuda()
     B = stats.shape[0]
-    sums = torch.zeros((n_levels, 3, 3), dtype=torch.float64, device=stats.device)
-    n_fail = torch.zeros((n_levels,), dtype=torch.float64, device=stats.device)
+    if out is not None:
+        sums, n_fail = out
+    else:
+        sums = torch.zeros((n_levels, 3, 3), dtype=torch.float64, device=stats.device)
+        n_fail = torch.zeros((n_levels,), dtype=torch.float64, device=stats.device)
     L.check(L.load().uvs_reduce_stats(B, int(trial0), int(sweep_epoch), int(n_levels), _ptr(stats), _ptr(status),
                                       _ptr(sums), _ptr(n_fail), _stream()), "uvs_reduce_stats")
     return sums, n_fail
