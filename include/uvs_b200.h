@@ -255,6 +255,20 @@ int uvs_twist_loop(const uvs_closed_loop_cfg* cfg, const uvs_twist_cfg* tw, uint
 int uvs_closed_loop_host(const uvs_closed_loop_cfg* cfg, uint64_t trial0, int64_t B,
                          double* stats_host, int32_t* status_host, int32_t* frames_host);
 
+/* Trajectory-log streaming — the batch form of main.py:152-196, which appends every experiment's T frame rows to
+ * results.csv: the [B,T,6+2m] log of a large job (53 GB for 10^6 trials of 300 frames) never exists in one piece.
+ * The batch runs as launches of `chunk` trials; each chunk's log goes to one of two device buffers, is copied to one
+ * of two page-locked host buffers on a second stream while the next chunk computes, and is handed to `sink` on the
+ * calling thread (which may format CSV rows, write a binary file, ...) while the GPU works on.
+ * sink(user, first_trial, n, log_host [n,T,6+2m], stats_host [n,3], status_host [n], frames_host [n]); the pointers are
+ * valid only during the call; a non-zero return stops the stream (UVS_ERR_INVALID).  sink may be NULL (measurement).
+ * Synchronous.  Optional host outputs: d2h_gbs = bytes copied / time the copy engine was busy (CUDA events on the copy
+ * stream), wall_s = duration of the whole call.  cfg->filt / noise / sweep as for uvs_closed_loop. */
+typedef int (*uvs_log_sink)(void* user, uint64_t first_trial, int64_t n, const double* log_host, const double* stats_host,
+                            const int32_t* status_host, const int32_t* frames_host);
+int uvs_closed_loop_stream(const uvs_closed_loop_cfg* cfg, uint64_t trial0, int64_t B, int64_t chunk,
+                           uvs_log_sink sink, void* user, double* d2h_gbs, double* wall_s);
+
 /* Per-noise-level sums for results/plot_errorbar.m:87-94: for level c and
  * statistic s in {ISE,IAE,ITAE}: sums[c][s] = {n_ok, sum x, sum x^2} over
  * SUCCESS trials, plus n_fail[c].  level = (trial0+b) / sweep_epoch (clamped).

@@ -289,3 +289,50 @@ def test_empty_ragged_and_degenerate_batches(uvs, mode):
     z = torch.empty((0, 6), dtype=torch.float64, device="cuda")
     assert E.ur10_fk(z)[0].shape == (0, 4, 4) and E.project(4, z)[0].shape == (0, 8)
     assert E.noise_fill(E.noise_params(L.NOISE_WHITE, seed=1, std=1.0), 0, 0, 10, 8).shape == (0, 10, 8)
+
+
+# ------------------------------------------------------------------ trajectory-log streaming
+def test_stream_matches_the_one_shot_log(uvs):
+    """uvs_closed_loop_stream: chunked launches, two device + two page-locked host buffers, the copy of a chunk overlapping
+    the next launch.  Every chunk handed to the sink equals the log / statistics of one big logged launch, ragged last
+    chunk included; a sink that asks to stop ends the stream with an error."""
+    L, E = uvs._lib, uvs.engine
+    p = E.filter_params(5, 4, mode=L.MODE_BLOCKDIAG, annealing=True)
+    cfg = E.closed_loop_cfg(p, E.noise_params(L.NOISE_ALPHA_STABLE, seed=11, alpha=1.4), T=300, dt=0.05, ibvs_gain=0.2,
+                            q_start=[0.0, 0.0, 1.96349541, 0.0, -1.57079633, 0.0], desired_f=DESIRED[4])
+    B, trial0 = 1000, 77
+    ref = E.closed_loop(cfg, trial0, B, want_log=True)
+    rlog, rst, rss, rfr = (ref[k].cpu().numpy() for k in ("log", "stats", "status", "frames"))
+    got = {"log": np.zeros_like(rlog), "stats": np.zeros_like(rst), "chunks": []}
+
+    def sink(first, log, st, ss, fr):
+        a = first - trial0
+        got["log"][a:a + len(st)] = log
+        got["stats"][a:a + len(st)] = st
+        got["chunks"].append((first, len(st)))
+        assert np.array_equal(ss, rss[a:a + len(st)]) and np.array_equal(fr, rfr[a:a + len(st)])
+
+    info = E.closed_loop_stream(cfg, trial0, B, chunk=192, sink=sink)
+    assert got["chunks"] == [(trial0 + 192 * i, min(192, B - 192 * i)) for i in range(6)]      # in order, ragged tail
+    assert np.array_equal(got["log"], rlog) and np.array_equal(got["stats"], rst)
+    assert info["d2h_gbs"] > 0.5 and info["wall_s"] > 0
+    with pytest.raises(L.UvsError):
+        E.closed_loop_stream(cfg, trial0, B, chunk=192, sink=lambda *a: True)
+    with pytest.raises(ZeroDivisionError):                                      # a sink's exception resurfaces in Python
+        E.closed_loop_stream(cfg, trial0, B, chunk=192, sink=lambda *a: 1 / 0)
+    assert E.closed_loop_stream(cfg, 0, 0)["wall_s"] == 0.0                     # empty batch
+
+
+def test_run_sweep_streams_every_experiment_to_csv(uvs, tmp_path):
+    """main.py:152-196 logs every experiment: csv_trials=None streams the whole sweep once (statistics and rows from the
+    same launches) and writes the rows with the vectorised writer; same table as the per-level logged launches."""
+    import pandas as pd
+    S = uvs.sweep
+    a, b = tmp_path / "stream.csv", tmp_path / "levels.csv"
+    res = S.run_sweep(_cfg("GMCKF"), epoch=3, csv_path=str(a), csv_trials=None, want_trials=True, stream_chunk=7)
+    res2 = S.run_sweep(_cfg("GMCKF"), epoch=3, csv_path=str(b), csv_trials=3, want_trials=True)
+    assert np.array_equal(res["stats"], res2["stats"]) and res["stream"]["rows"] == int(36 * 300)
+    da, db = pd.read_csv(a), pd.read_csv(b)
+    assert list(da.columns) == REFERENCE_COLUMNS and len(da) == len(db) == 36 * 300
+    assert da.equals(db)
+    assert sorted(da["experiment_id"].unique()) == list(range(36))

@@ -189,3 +189,34 @@ def test_published_tables_parse_and_servo_rate():
     v = CL.servo_rate(cfg, np.array([4.0, -0.1, 0.3]), np.array([0.0, 0.0, 0.2]))
     assert np.allclose(v, [0.2, -0.05, 0.15])          # lag 0.5, then |dv| <= a_max dt = 0.2, then |v| <= 1
     assert np.allclose(CL.servo_rate(dict(dt=0.05), np.array([3.0]), np.array([0.0])), [3.0])      # no limits: kinematic
+
+
+def test_shipped_config_is_the_reference_configuration():
+    """`python main.py` runs bare, as /root/reference/main.py:16 does: the repository ships a config.json with the
+    reference's values (SURVEY.md section 5 lists every key)."""
+    with open(os.path.join(ROOT, "config.json")) as fh:
+        shipped = json.load(fh)
+    assert shipped == BASE_CONFIG
+    run = sweep.load_config(os.path.join(ROOT, "config.json"))
+    assert run["epoch"] == 100 and run["method"] == uvs_b200.Method.MCKF
+
+
+def test_bench_plan_shards_like_the_driver():
+    """bench.py: N = 1 -> configs[2] (100 000 trials, weak); N > 1 -> configs[3] (1 000 000 trials sharded, strong) with
+    the contiguous ranges of sweep.shard_range; --trials forces a fixed count per GPU."""
+    import argparse
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(ROOT, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    a = argparse.Namespace(trials=None, total_trials=None)
+    assert bench.plan(a, 0, 1) == (100_000, 0, 100_000, "weak")
+    for world in (2, 4, 8, 3):
+        got = [bench.plan(a, r, world) for r in range(world)]
+        assert all(g[3] == "strong" and g[2] == 1_000_000 for g in got)
+        assert [(g[1], g[1] + g[0]) for g in got] == [sweep.shard_range(1_000_000, r, world) for r in range(world)]
+        assert sum(g[0] for g in got) == 1_000_000
+    a = argparse.Namespace(trials=5000, total_trials=None)
+    assert bench.plan(a, 3, 4) == (5000, 15000, 20000, "weak")
+    a = argparse.Namespace(trials=None, total_trials=96_000)
+    assert bench.plan(a, 0, 1) == (96_000, 0, 96_000, "strong")

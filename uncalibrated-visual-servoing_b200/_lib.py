@@ -61,6 +61,11 @@ class TwistCfg(C.Structure):
                 ("err_threshold", C.c_double)]
 
 
+# int sink(void* user, uint64_t first_trial, int64_t n, const double* log, const double* stats, const int32_t* status,
+#          const int32_t* frames)  — include/uvs_b200.h: uvs_log_sink
+LOG_SINK = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_uint64, C.c_int64, C.POINTER(C.c_double), C.POINTER(C.c_double),
+                       C.POINTER(C.c_int32), C.POINTER(C.c_int32))
+
 _PROTOTYPES = {
     "uvs_version": ([], C.c_int),
     "uvs_last_error": ([C.c_char_p, C.c_size_t], C.c_int),
@@ -80,6 +85,8 @@ _PROTOTYPES = {
                         _dp], C.c_int),
     "uvs_closed_loop_host": ([C.POINTER(ClosedLoopCfg), C.c_uint64, C.c_int64, C.POINTER(C.c_double),
                               C.POINTER(C.c_int32), C.POINTER(C.c_int32)], C.c_int),
+    "uvs_closed_loop_stream": ([C.POINTER(ClosedLoopCfg), C.c_uint64, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p,
+                                C.POINTER(C.c_double), C.POINTER(C.c_double)], C.c_int),
     "uvs_reduce_stats": ([C.c_int64, C.c_uint64, C.c_int32, C.c_int32, _dp, _dp, _dp, _dp, _dp], C.c_int),
     "uvs_fp64_peak": ([C.c_int32, C.POINTER(C.c_double), C.POINTER(C.c_double)], C.c_int),
 }

@@ -1,5 +1,6 @@
 // api.cu — the extern "C" boundary of libuvs_b200.so (declared in include/uvs_b200.h).
 // Argument validation, kernel-family selection, launch geometry, error plumbing.
+#include <chrono>
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
@@ -322,6 +323,108 @@ int uvs_closed_loop_host(const uvs_closed_loop_cfg* cfg, uint64_t trial0, int64_
         rc = check_cuda(cudaMemcpyAsync(frames_host, d_frames, n_i32, cudaMemcpyDeviceToHost, st), "D2H frames");
     const int rc_sync = check_cuda(cudaStreamSynchronize(st), "uvs_closed_loop_host");
     return rc ? rc : rc_sync;
+}
+
+int uvs_closed_loop_stream(const uvs_closed_loop_cfg* cfg, uint64_t trial0, int64_t B, int64_t chunk,
+                           uvs_log_sink sink, void* user, double* d2h_gbs, double* wall_s) {
+    if (!cfg || B < 0 || chunk < 1) return set_error(UVS_ERR_INVALID, "uvs_closed_loop_stream: bad argument");
+    if (!valid_nf(cfg->filt.nf)) return set_error(UVS_ERR_INVALID, "nf must be 1, 3 or 4 (got %d)", cfg->filt.nf);
+    if (cfg->T < 1) return set_error(UVS_ERR_INVALID, "T=%d", cfg->T);
+    if (d2h_gbs) *d2h_gbs = 0.0;
+    if (wall_s) *wall_s = 0.0;
+    if (B == 0) return 0;
+    if (chunk > B) chunk = B;
+    const int m = 2 * cfg->filt.nf, logw = 6 + 2 * m;
+    const size_t n_log = sizeof(double) * (size_t)chunk * cfg->T * logw, n_stats = sizeof(double) * 3 * (size_t)chunk,
+                 n_i32 = sizeof(int32_t) * (size_t)chunk;
+    const size_t bytes = n_log + n_stats + 2 * n_i32;
+    struct Slot {
+        unsigned char *dev = nullptr, *host = nullptr;
+        cudaEvent_t computed = nullptr, copy_begin = nullptr, copied = nullptr;
+        long long first = 0, n = 0;
+    } slot[2];
+    cudaStream_t compute = nullptr, copy = nullptr;
+    int rc = 0;
+    auto fail = [&](cudaError_t e, const char* what) { if (!rc && e != cudaSuccess) rc = check_cuda(e, what); return rc != 0; };
+    fail(cudaStreamCreateWithFlags(&compute, cudaStreamNonBlocking), "stream");
+    fail(cudaStreamCreateWithFlags(&copy, cudaStreamNonBlocking), "stream");
+    for (int i = 0; i < 2 && !rc; ++i) {
+        fail(cudaMalloc((void**)&slot[i].dev, bytes), "cudaMalloc log slot");
+        fail(cudaHostAlloc((void**)&slot[i].host, bytes, cudaHostAllocDefault), "cudaHostAlloc log slot");
+        fail(cudaEventCreate(&slot[i].computed), "event");
+        fail(cudaEventCreate(&slot[i].copy_begin), "event");
+        fail(cudaEventCreate(&slot[i].copied), "event");
+    }
+    auto ptrs = [&](unsigned char* base, double*& log, double*& stats, int32_t*& status, int32_t*& frames) {
+        log = reinterpret_cast<double*>(base);
+        stats = reinterpret_cast<double*>(base + n_log);
+        status = reinterpret_cast<int32_t*>(base + n_log + n_stats);
+        frames = reinterpret_cast<int32_t*>(base + n_log + n_stats + n_i32);
+    };
+    double copy_ms = 0.0, copied_bytes = 0.0;
+    // drain slot s: wait for its copy, account the copy-engine time, hand the chunk to the sink
+    auto drain = [&](Slot& s) {
+        if (s.n == 0 || rc) return;
+        if (fail(cudaEventSynchronize(s.copied), "log D2H")) return;
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, s.copy_begin, s.copied);
+        copy_ms += ms;
+        double *log, *stats; int32_t *status, *frames;
+        ptrs(s.host, log, stats, status, frames);
+        copied_bytes += (double)(sizeof(double) * (size_t)s.n * cfg->T * logw + sizeof(double) * 3 * s.n + 2 * sizeof(int32_t) * s.n);
+        if (sink && sink(user, (uint64_t)s.first, s.n, log, stats, status, frames) != 0)
+            rc = set_error(UVS_ERR_INVALID, "uvs_closed_loop_stream: the sink asked to stop at trial %lld", s.first);
+        s.n = 0;
+    };
+    const auto t_begin = std::chrono::steady_clock::now();        // after the allocations: the steady-state pipeline
+    long long done = 0;
+    for (int it = 0; done < B && !rc; ++it) {
+        Slot& s = slot[it & 1];
+        drain(s);                                       // its previous chunk (two launches ago) must have left the buffers
+        if (rc) break;
+        const long long n = (B - done < chunk) ? (B - done) : chunk;
+        double *log, *stats; int32_t *status, *frames;
+        ptrs(s.dev, log, stats, status, frames);
+        uvs_closed_loop_io io{};
+        io.stats = stats; io.status = status; io.frames = frames; io.log = log;
+        if ((rc = uvs_closed_loop(cfg, trial0 + (uint64_t)done, n, &io, compute)) != 0) break;
+        fail(cudaEventRecord(s.computed, compute), "event record");
+        fail(cudaStreamWaitEvent(copy, s.computed, 0), "stream wait");
+        fail(cudaEventRecord(s.copy_begin, copy), "event record");
+        // one contiguous copy: the chunk's log, stats, status and frames are laid out back to back (a short last chunk
+        // copies its own log prefix and the three small arrays separately)
+        if (n == chunk) fail(cudaMemcpyAsync(s.host, s.dev, bytes, cudaMemcpyDeviceToHost, copy), "log D2H");
+        else {
+            fail(cudaMemcpyAsync(s.host, s.dev, sizeof(double) * (size_t)n * cfg->T * logw, cudaMemcpyDeviceToHost, copy), "log D2H");
+            fail(cudaMemcpyAsync(s.host + n_log, s.dev + n_log, n_stats + 2 * n_i32, cudaMemcpyDeviceToHost, copy), "log D2H");
+        }
+        fail(cudaEventRecord(s.copied, copy), "event record");
+        s.first = (long long)trial0 + done;
+        s.n = n;
+        done += n;
+        drain(slot[(it + 1) & 1]);                      // the other slot's chunk: sink it while this one computes
+    }
+    drain(slot[0]);
+    drain(slot[1]);
+    if (!rc) {
+        fail(cudaStreamSynchronize(copy), "uvs_closed_loop_stream");
+        fail(cudaStreamSynchronize(compute), "uvs_closed_loop_stream");
+        if (wall_s) *wall_s = std::chrono::duration<double>(std::chrono::steady_clock::now() - t_begin).count();
+        if (d2h_gbs && copy_ms > 0.0) *d2h_gbs = copied_bytes / (copy_ms * 1e-3) / 1e9;
+    } else {
+        cudaStreamSynchronize(copy);
+        cudaStreamSynchronize(compute);
+    }
+    for (int i = 0; i < 2; ++i) {
+        if (slot[i].dev) cudaFree(slot[i].dev);
+        if (slot[i].host) cudaFreeHost(slot[i].host);
+        if (slot[i].computed) cudaEventDestroy(slot[i].computed);
+        if (slot[i].copy_begin) cudaEventDestroy(slot[i].copy_begin);
+        if (slot[i].copied) cudaEventDestroy(slot[i].copied);
+    }
+    if (compute) cudaStreamDestroy(compute);
+    if (copy) cudaStreamDestroy(copy);
+    return rc;
 }
 
 int uvs_reduce_stats(int64_t B, uint64_t trial0, int32_t sweep_epoch, int32_t n_levels,

@@ -297,6 +297,37 @@ def closed_loop_host(cfg, trial0, B, pinned=True):
     return stats, status, frames
 
 
+def closed_loop_stream(cfg, trial0, B, chunk=4096, sink=None):
+    """Streams the trajectory log of B closed-loop trials to the host in chunks (uvs_closed_loop_stream: two device and
+    two page-locked host buffers, the copy of chunk i overlaps the launch of chunk i + 1).  ``sink(first_trial, log, stats,
+    status, frames)`` receives numpy VIEWS of the page-locked buffers (log [n,T,6+2m]), valid during the call only; a
+    truthy return value stops the stream.  Returns dict(d2h_gbs, wall_s)."""
+    _require_cuda()
+    m = 2 * cfg.filt.nf
+    T, W = cfg.T, 6 + 2 * m
+    err = []
+
+    def _sink(user, first, n, log, stats, status, frames):
+        try:
+            n = int(n)
+            stop = sink(int(first), np.ctypeslib.as_array(log, shape=(n, T, W)), np.ctypeslib.as_array(stats, shape=(n, 3)),
+                        np.ctypeslib.as_array(status, shape=(n,)), np.ctypeslib.as_array(frames, shape=(n,)))
+            return 1 if stop else 0
+        except BaseException as e:           # never let an exception cross the C boundary
+            err.append(e)
+            return 1
+
+    cb = L.LOG_SINK(_sink) if sink is not None else None
+    gbs, wall = C.c_double(0), C.c_double(0)
+    rc = L.load().uvs_closed_loop_stream(C.byref(cfg), int(trial0), int(B), int(chunk),
+                                         C.cast(cb, C.c_void_p) if cb is not None else None, None,
+                                         C.byref(gbs), C.byref(wall))
+    if err:
+        raise err[0]
+    L.check(rc, "uvs_closed_loop_stream")
+    return dict(d2h_gbs=gbs.value, wall_s=wall.value)
+
+
 def reduce_stats(stats, status, trial0, sweep_epoch, n_levels, out=None):
     """Per-level sums [n_levels,3,3] = {n_ok, sum, sum of squares} and n_fail [n_levels].  ``out`` = (sums, n_fail)
     to ACCUMULATE into existing buffers (e.g. two views of one packed tensor that is all-reduced once)."""

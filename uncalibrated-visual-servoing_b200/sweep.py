@@ -179,38 +179,96 @@ def level_quantiles(stats, status, epoch, n_levels, q=(0.25, 0.5, 0.75)):
 
 
 # ------------------------------------------------------------------------------------- CSV
-def write_results_csv(path, experiment_ids, status, rho, logs, frames, desired_f, dt, kernel_bw_log=None,
-                      header=True, append=False):
-    """Appends the frame logs of the given trials in the reference schema (main.py:152-196): one row per
-    frame, experiment constants repeated on every row, ``status`` spelled like the enum's ``str()``.
+def results_frame(experiment_ids, status, rho, logs, frames, desired_f, dt, kernel_bw_log=None):
+    """The rows main.py:152-194 appends for the given trials, as ONE pandas DataFrame built column-wise (no Python
+    loop over rows): experiment constants repeated on every frame row, ``status`` spelled like the enum's ``str()``.
 
-    logs: [n, T, 6 + 2m] (q, f, noise) as produced by the closed-loop kernels; frames[n] = rows to emit."""
+    logs: [n, T, 6 + 2m] (q, f, noise) as produced by the closed-loop kernels; frames[n] = rows to emit per trial."""
+    import pandas as pd
     from .experiment import ExperimentStatus
     from .ur10_simulation import camera_log_from_q
     logs = np.asarray(logs, dtype=float)
-    m = (logs.shape[2] - 6) // 2
-    desired = [float(v) for v in desired_f]
-    mode = "a" if append else "w"
-    with open(path, mode, newline="", encoding="utf-8") as fh:
-        w = csv.writer(fh)
-        if header:
-            w.writerow(csv_columns(m))
-        for i, eid in enumerate(experiment_ids):
-            k = int(frames[i])
-            q_log, f_log, nz_log = logs[i, :k, 0:6], logs[i, :k, 6:6 + m], logs[i, :k, 6 + m:6 + 2 * m]
-            cam = camera_log_from_q(q_log)
-            st = str(ExperimentStatus(int(status[i])))
-            bw = -np.ones(k) if kernel_bw_log is None else np.asarray(kernel_bw_log[i], dtype=float)[:k]
-            for r in range(k):
-                w.writerow([int(eid), st, repr(float(rho[i])), repr(float((r + 1) * dt))] +
-                           [repr(float(v)) for v in q_log[r]] + [repr(float(v)) for v in cam[r]] +
-                           [repr(float(v)) for v in f_log[r]] + [repr(v) for v in desired] +
-                           [repr(float(v)) for v in nz_log[r]] + [repr(float(bw[r]))])
+    n, T, W = logs.shape
+    m = (W - 6) // 2
+    frames = np.asarray(frames, dtype=np.int64)
+    keep = (np.arange(T)[None, :] < frames[:, None])                       # [n,T] rows a trial actually ran
+    rows = logs[keep]                                                      # [R, W], trial-major then frame order
+    trial_of = np.repeat(np.arange(n), frames)
+    frame_of = np.nonzero(keep)[1]
+    names = {int(e.value): str(e) for e in ExperimentStatus}
+    data = {"experiment_id": np.asarray(experiment_ids, dtype=np.int64)[trial_of],
+            "status": np.array([names[int(v)] for v in np.asarray(status)], dtype=object)[trial_of],
+            "rho": np.asarray(rho, dtype=float)[trial_of],
+            "t": (frame_of + 1) * float(dt)}
+    cam = camera_log_from_q(rows[:, 0:6])                                  # experiment.py:324, one batched FK launch
+    for i in range(6):
+        data[f"q_{i + 1}"] = rows[:, i]
+    for i, name in enumerate(("camera_x", "camera_y", "camera_z", "camera_roll", "camera_pitch", "camera_yaw")):
+        data[name] = cam[:, i]
+    for i in range(m):
+        data[f"f_{i + 1}"] = rows[:, 6 + i]
+    for i in range(m):
+        data[f"desired_f_{i + 1}"] = np.full(len(rows), float(desired_f[i]))
+    for i in range(m):
+        data[f"noise_{i + 1}"] = rows[:, 6 + m + i]
+    if kernel_bw_log is None:
+        data["kernel_bw"] = -np.ones(len(rows))
+    else:
+        data["kernel_bw"] = np.asarray(kernel_bw_log, dtype=float)[:, :T][keep]
+    return pd.DataFrame(data, columns=csv_columns(m))
+
+
+def write_results_csv(path, experiment_ids, status, rho, logs, frames, desired_f, dt, kernel_bw_log=None,
+                      header=True, append=False):
+    """Appends the frame logs of the given trials in the reference schema (main.py:152-196), through the same
+    ``DataFrame.to_csv(mode='a', index=False)`` call the reference makes — so numbers are formatted identically."""
+    df = results_frame(experiment_ids, status, rho, logs, frames, desired_f, dt, kernel_bw_log)
+    df.to_csv(path, mode="a" if append else "w", index=False, header=header)
+    return len(df)
+
+
+def stream_results(cfg, lo, hi, levels, epoch, csv_path=None, npy_path=None, chunk=4096, kernel_bw_row=None,
+                   desired_f=None, dt=0.05, header=True):
+    """Runs trials [lo, hi) once with the trajectory log STREAMED to the host (engine.closed_loop_stream) and consumed
+    chunk by chunk while the GPU computes the next chunk: rows appended to ``csv_path`` in the reference schema and/or
+    the raw [n,T,6+2m] log written to ``npy_path`` (a .npy memory map — the format for jobs whose CSV would be
+    hundreds of GB).  Returns (stats [n,3], status [n], frames [n], info) with the streaming rates."""
+    from . import engine
+    n = hi - lo
+    m = 2 * cfg.filt.nf
+    stats = np.zeros((n, 3)); status = np.zeros(n, dtype=np.int32); frames = np.zeros(n, dtype=np.int32)
+    mm = None
+    if npy_path is not None:
+        mm = np.lib.format.open_memmap(npy_path, mode="w+", dtype=np.float64, shape=(n, cfg.T, 6 + 2 * m))
+    state = {"header": header, "rows": 0, "csv_s": 0.0}
+
+    def sink(first, log, st, ss, fr):
+        import time
+        a, b = first - lo, first - lo + len(st)
+        stats[a:b], status[a:b], frames[a:b] = st, ss, fr
+        if mm is not None:
+            mm[a:b] = log
+        if csv_path is not None:
+            t0 = time.perf_counter()
+            ids = np.arange(first, first + len(st))
+            lvl = np.minimum(ids // max(int(epoch), 1), len(levels) - 1)
+            bw = None if kernel_bw_row is None else np.tile(kernel_bw_row, (len(st), 1))
+            state["rows"] += write_results_csv(csv_path, ids, ss, np.asarray(levels)[lvl], log, fr, desired_f, dt,
+                                               kernel_bw_log=bw, header=state["header"], append=not state["header"])
+            state["header"] = False
+            state["csv_s"] += time.perf_counter() - t0
+        return 0
+
+    info = engine.closed_loop_stream(cfg, lo, n, chunk=chunk, sink=sink)
+    if mm is not None:
+        mm.flush()
+    info.update(rows=state["rows"], csv_s=state["csv_s"], log_bytes=int(frames.sum()) * (6 + 2 * m) * 8)
+    return stats, status, frames, info
 
 
 # ------------------------------------------------------------------------------------- the sweep
 def run_sweep(config, *, epoch=None, csv_path=None, csv_trials=0, want_trials=False, mode=None, group=None,
-              logger=None):
+              logger=None, stream_chunk=4096):
     """Runs the whole main.py queue (12 levels x epoch experiments) on this process group's GPUs.
 
     Returns, on every rank: ``levels`` (rho / alpha values), ``summary`` (per-level mean/std, counts),
@@ -242,7 +300,35 @@ def run_sweep(config, *, epoch=None, csv_path=None, csv_trials=0, want_trials=Fa
                           pose_seed=run["experiment_seed"] if run["experiment_seed"] is not None else 0,
                           sweep=levels, sweep_epoch=ep, sweep_param=run["sweep_param"], method_params=mp)
     log.info("Experiments %d..%d of %d on rank %d/%d", lo, hi, n_trials, rank, world)
-    out = exp.run(to_host=False)
+    T = int(run["t_max"] / run["dt"])
+    bw_row = None
+    if run["method"] == Method.MCKF:                        # experiment.py:330: only MCKF logs its bandwidth
+        kk = np.arange(T)
+        bw_row = mp["kernel_bw"] + (100.0 * (1 - kk / T) if mp.get("annealing") else 0.0 * kk)
+    streamed = csv_path is not None and csv_trials is None
+    stream_info = None
+    if streamed:
+        # main.py:152-196 logs EVERY experiment: one pass, the log streamed through page-locked buffers while the
+        # next chunk computes; every rank writes its own contiguous part, rank 0 stitches them in rank order
+        part = csv_path if world == 1 else f"{csv_path}.part{rank}"
+        st_h, ss_h, fr_h, stream_info = stream_results(exp.config(), lo, hi, levels, ep, csv_path=part, chunk=stream_chunk,
+                                                       kernel_bw_row=bw_row, desired_f=run["desired_f"], dt=run["dt"],
+                                                       header=(rank == 0))
+        out = {"stats": engine.dev(st_h), "status": engine.dev(ss_h, dtype=torch.int32)}
+        if world > 1:
+            dist.barrier(group)
+            if rank == 0:
+                with open(csv_path, "wb") as dst:
+                    for r in range(world):
+                        with open(f"{csv_path}.part{r}", "rb") as src:
+                            while True:
+                                buf = src.read(1 << 24)
+                                if not buf:
+                                    break
+                                dst.write(buf)
+                        os.remove(f"{csv_path}.part{r}")
+    else:
+        out = exp.run(to_host=False)
     sums, n_fail = engine.reduce_stats(out["stats"], out["status"], lo, ep, len(levels))
     merge_level_sums(sums, n_fail, group)
     result = {"levels": levels, "sweep_param": run["sweep_param"], "epoch": ep, "n_trials": n_trials,
@@ -251,11 +337,12 @@ def run_sweep(config, *, epoch=None, csv_path=None, csv_trials=0, want_trials=Fa
         st, ss = gather_trials(out["stats"], out["status"], group)
         result["stats"], result["status"] = st.cpu().numpy(), ss.cpu().numpy()
         result["quantiles"] = level_quantiles(result["stats"], result["status"], ep, len(levels))
-    if csv_path is not None and rank == 0:
-        per = ep if csv_trials is None else min(int(csv_trials), ep)
+    if stream_info is not None:
+        result["stream"] = stream_info
+    if csv_path is not None and rank == 0 and not streamed:
+        per = min(int(csv_trials), ep)
         ids = [lv * ep + i for lv in range(len(levels)) for i in range(per)]
         header = True
-        T = int(run["t_max"] / run["dt"])
         for lv in range(len(levels)):                       # one small logged launch per level: bounded memory
             chunk = [k for k in ids if k // ep == lv]
             if not chunk:
@@ -265,11 +352,7 @@ def run_sweep(config, *, epoch=None, csv_path=None, csv_trials=0, want_trials=Fa
                                  change_q_start=run["change_q_start"], pose_seed=exp.pose_seed, sweep=levels,
                                  sweep_epoch=ep, sweep_param=run["sweep_param"], method_params=mp)
             o = e2.run(want_log=True)
-            bw = None
-            if run["method"] == Method.MCKF:                # experiment.py:330
-                kk = np.arange(T)
-                row = mp["kernel_bw"] + (100.0 * (1 - kk / T) if mp.get("annealing") else 0.0 * kk)
-                bw = np.tile(row, (len(chunk), 1))
+            bw = None if bw_row is None else np.tile(bw_row, (len(chunk), 1))
             write_results_csv(csv_path, chunk, o["status"], [levels[lv]] * len(chunk), o["log"], o["frames"],
                               run["desired_f"], run["dt"], kernel_bw_log=bw, header=header, append=not header)
             header = False
@@ -285,7 +368,9 @@ def main(argv=None):
     import argparse
     import time
     ap = argparse.ArgumentParser(description=main.__doc__)
-    ap.add_argument("--config", default="config.json")
+    ap.add_argument("--config", default=None,
+                    help="config.json (default: ./config.json as main.py:16 reads it, else the copy shipped beside this "
+                         "package, which equals the reference's)")
     ap.add_argument("--out", default=None, help="output directory (default results/data/<timestamp>)")
     ap.add_argument("--epoch", type=int, default=None, help="override experiments.epoch")
     ap.add_argument("--csv-trials", type=int, default=None,
@@ -306,7 +391,11 @@ def main(argv=None):
         ch = logging.StreamHandler(sys.stdout)
         ch.setFormatter(logging.Formatter('[%(levelname)s] %(asctime)s - %(name)s - %(message)s'))
         logger.addHandler(ch)
-    with open(a.config, "r", encoding="utf-8") as fh:
+    cfg_path = a.config
+    if cfg_path is None:
+        here = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "config.json")
+        cfg_path = "config.json" if os.path.exists("config.json") else here
+    with open(cfg_path, "r", encoding="utf-8") as fh:
         cfg = json.load(fh)
     logger.handlers[0].setLevel(getattr(logging, str(cfg.get("log_level", "INFO")), logging.INFO))
     if rank == 0:

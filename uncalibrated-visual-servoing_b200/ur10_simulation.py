@@ -35,6 +35,7 @@ class UR10Simulation:
         self.q = np.zeros(6)
         self.dq = np.zeros(6)
         self._q_cmd = np.zeros(6)
+        self._T06 = self._Jg = self._q_fk = None      # cached transforms (ur10_simulation.py:59,97-110)
         self.steps = 0
         self.visualization = visualization
         self.sim = _Sim(self)
@@ -51,6 +52,7 @@ class UR10Simulation:
         self._q_cmd = self.q.copy()
         self.steps = 0
         self.step()
+        self.fkine(recalculate=True, all_transforms=True)          # ur10_simulation.py:59
 
     def stop(self):
         pass
@@ -69,33 +71,63 @@ class UR10Simulation:
     def getJointsVel(self):
         return self.dq
 
-    # -- analytic kinematics (ur10_simulation.py:97-195) on the GPU ---------------------------
-    def _fk(self):
+    # -- analytic kinematics (ur10_simulation.py:97-195) -----------------------------------------
+    # Like the reference, the transforms are CACHED: fkine(recalculate=True) reads the joints and refreshes them
+    # (ur10_simulation.py:97-105), start() ends with such a refresh (:59), and every other accessor works on the cache
+    # unless asked to recalculate — a script that calls jacobian() / getCameraRotation() without the flag gets the pose
+    # of the last refresh, exactly as with the reference object.  T_0_6 and the geometric Jacobian come from
+    # uvs_ur10_fk; the intermediate T_0_1..T_0_5 (all_transforms=True, used by nothing on the hot path) are the same
+    # DH products evaluated on the host.
+    _DH = ((0.0, 0.128, 0.0, -np.pi / 2), (-np.pi / 2, 0.0, 0.6127, 0.0), (0.0, 0.0, 0.5716, 0.0),
+           (-np.pi / 2, 0.1639, 0.0, -np.pi / 2), (0.0, 0.1157, 0.0, np.pi / 2), (np.pi, 0.0922, 0.0, 0.0))
+
+    @staticmethod
+    def dh(theta, d, a, alpha):
+        """ur10_simulation.py:204-211: Rz(theta) Tz(d) Tx(a) Rx(alpha)."""
+        ct, st, ca, sa = np.cos(theta), np.sin(theta), np.cos(alpha), np.sin(alpha)
+        return np.array([[ct, -st * ca, st * sa, a * ct], [st, ct * ca, -ct * sa, a * st],
+                         [0.0, sa, ca, d], [0.0, 0.0, 0.0, 1.0]])
+
+    def _refresh(self):
         T06, Jg = engine.ur10_fk(engine.dev(self.q.reshape(1, 6)))
-        return T06[0].cpu().numpy(), Jg[0].cpu().numpy()
+        self._T06, self._Jg = T06[0].cpu().numpy(), Jg[0].cpu().numpy()
+        self._q_fk = self.q.copy()
+
+    def _cached(self, recalculate):
+        if recalculate or self._T06 is None:
+            self._refresh()
+        return self._T06, self._Jg
 
     def fkine(self, recalculate=False, all_transforms=False):
-        if all_transforms:
-            raise NotImplementedError("intermediate transforms are not exposed; use jacobian()")
-        return self._fk()[0]
+        T06, _ = self._cached(recalculate)
+        if not all_transforms:
+            return T06
+        Ts, T = [], np.eye(4)
+        for i, (off, d, a, alpha) in enumerate(self._DH):          # ur10_simulation.py:100-105
+            T = T @ self.dh(self._q_fk[i] + off, d, a, alpha)
+            Ts.append(T)
+        Ts[5] = T06
+        return tuple(reversed(Ts))                                  # T_0_6, T_0_5, ..., T_0_1 (:107-108)
 
     def jacobian(self, recalculate_fkine=False):
-        return self._fk()[1]
+        return self._cached(recalculate_fkine)[1]
 
     def getCameraRotation(self, recalculate_fkine=False):
-        return self._fk()[0][0:3, 0:3]
+        return self._cached(recalculate_fkine)[0][0:3, 0:3]
 
     def getCameraHeight(self, recalculate_fkine=False):
-        return self._fk()[0][2, 3]
+        return self._cached(recalculate_fkine)[0][2, 3]
 
     def getCameraPosition(self, recalculate_fkine=False):
-        return self._fk()[0][0:3, 3]
+        return self._cached(recalculate_fkine)[0][0:3, 3]
 
     def computePose(self, recalculate_fkine=False):
-        return camera_pose_from_T(self._fk()[0][None])[0]
+        # the reference asks the simulator for the sensor pose (ur10_simulation.py:156-168): always the current joints
+        T06, _ = engine.ur10_fk(engine.dev(self.q.reshape(1, 6)), want_jacobian=False)
+        return camera_pose_from_T(T06.cpu().numpy())[0]
 
     def computeZ(self, n=1, recalculate_fkine=False):
-        t = self.getCameraPosition()
+        t = self.getCameraPosition(recalculate_fkine)
         return np.array([np.linalg.norm(t - self.targets[i]) for i in range(n)])
 
     def getCameraImage(self):
