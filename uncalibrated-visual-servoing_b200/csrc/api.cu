@@ -65,6 +65,14 @@ static int resolve_mode(const uvs_filter_params& fp, bool p_is_blocks_or_identit
 
 }  // namespace uvs
 
+#ifdef UVS_PHASE_CLOCKS
+static unsigned long long* g_phase_clk = nullptr;      // device array, profiling build only
+static unsigned long long* phase_clk_buffer() {
+    if (!g_phase_clk) { cudaMalloc((void**)&g_phase_clk, sizeof(unsigned long long) * UVS_NPHASE); cudaMemset(g_phase_clk, 0, sizeof(unsigned long long) * UVS_NPHASE); }
+    return g_phase_clk;
+}
+#endif
+
 using namespace uvs;
 
 #pragma GCC visibility push(default)
@@ -239,6 +247,9 @@ int uvs_closed_loop(const uvs_closed_loop_cfg* cfg, uint64_t trial0, int64_t B,
     if (mode < 0) return set_error(UVS_ERR_INVALID, "UVS_MODE_BLOCKDIAG needs Q = R = P0 = NULL");
     ClosedLoopArgs a{};
     a.cfg = *cfg; a.io = *io; a.trial0 = trial0; a.B = B;
+#ifdef UVS_PHASE_CLOCKS
+    a.phase_clk = phase_clk_buffer();
+#endif
     cudaStream_t st = (cudaStream_t)stream;
     if (mode == UVS_MODE_BLOCKDIAG) return check_cuda(launch_blockdiag_closed_loop(m, a, d.sms, st), "blockdiag closed loop");
     cudaError_t e;
@@ -436,6 +447,16 @@ int uvs_reduce_stats(int64_t B, uint64_t trial0, int32_t sweep_epoch, int32_t n_
     return check_cuda(launch_reduce_stats(B, trial0, sweep_epoch, n_levels, stats, status, sums, n_fail,
                                           (cudaStream_t)stream), "reduce_stats");
 }
+
+#ifdef UVS_PHASE_CLOCKS
+// profiling build only: read (and reset) the per-phase clock totals of the dense closed-loop kernel
+int uvs_debug_phase_clocks(unsigned long long* out_host, int reset) {
+    cudaDeviceSynchronize();
+    if (out_host) cudaMemcpy(out_host, phase_clk_buffer(), sizeof(unsigned long long) * UVS_NPHASE, cudaMemcpyDeviceToHost);
+    if (reset) cudaMemset(phase_clk_buffer(), 0, sizeof(unsigned long long) * UVS_NPHASE);
+    return 0;
+}
+#endif
 
 int uvs_fp64_peak(int32_t iters, double* tflops_host, double* ms_host) {
     if (!tflops_host || iters < 1) return set_error(UVS_ERR_INVALID, "uvs_fp64_peak: bad argument");

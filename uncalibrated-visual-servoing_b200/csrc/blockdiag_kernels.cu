@@ -265,9 +265,11 @@ __global__ void __launch_bounds__(128) bd_replay_kernel(const __grid_constant__ 
     }
 }
 
-// SERVO: the joint servo limits (cfg.v_max / a_max) are a separate instantiation so that the kinematic plant does not
-// carry the six executed-rate registers through the frame loop
-template <int M, int METHOD, bool SERVO>
+// EXTRAS: the joint servo limits (cfg.v_max / a_max / servo_gain), the per-frame trace and the dq_in replay gate
+// (uvs_closed_loop_io, ABI 4) live in a separate instantiation, so that the production launch — kinematic plant, no trace —
+// does not carry their registers through the frame loop (everything of this family is register-resident: the trace code
+// alone took the kernel from 332 to 786 bytes of spill stores and cost 8-15 % of throughput when it was unconditional)
+template <int M, int METHOD, bool EXTRAS>
 __global__ void __launch_bounds__(128, UVS_BD_MINB) bd_closed_loop_kernel(const __grid_constant__ ClosedLoopArgs a) {
     constexpr int GS = GroupSize<M>::value, GPW = 32 / GS, N = 6 * M, LOGW = 6 + 2 * M;
     constexpr int WPC = 4;
@@ -343,13 +345,13 @@ __global__ void __launch_bounds__(128, UVS_BD_MINB) bd_closed_loop_kernel(const 
         HoldState hs;
         double ise = 0.0, iae = 0.0, itae = 0.0;
         double dq[6] = {0, 0, 0, 0, 0, 0};
-        constexpr bool servo = SERVO;
-        double v_prev[6] = {0, 0, 0, 0, 0, 0};      // joint rates executed in the previous frame (SERVO only)
+        constexpr bool servo = EXTRAS;
+        double v_prev[6] = {0, 0, 0, 0, 0, 0};      // joint rates executed in the previous frame (EXTRAS only)
         int status = UVS_STATUS_SUCCESS, frames = 0, flags_all = 0;
         bool alive = trial_ok;
         const double desired = cfg.desired_f[row];
-        const bool traced = a.io.X_log != nullptr || a.io.P_log != nullptr || a.io.dq_log != nullptr ||
-                            a.io.kappa_log != nullptr || a.io.flags_log != nullptr;
+        const bool traced = EXTRAS && (a.io.X_log != nullptr || a.io.P_log != nullptr || a.io.dq_log != nullptr ||
+                                       a.io.kappa_log != nullptr || a.io.flags_log != nullptr);
 
         for (int k = 0; k < T; ++k) {
             if (!__any_sync(UVS_FULL_MASK, alive)) break;
@@ -414,7 +416,7 @@ __global__ void __launch_bounds__(128, UVS_BD_MINB) bd_closed_loop_kernel(const 
                     ise += e * e; iae += fabs(e); itae += t * fabs(e);
                 }
                 ++frames;
-                if (traced && trial_ok) {                                // per-frame trace (uvs_closed_loop_io, ABI 4)
+                if (EXTRAS && traced && trial_ok) {                      // per-frame trace (uvs_closed_loop_io, ABI 4)
                     const size_t bt = (size_t)b * T + k;
                     if (own) {
                         if (a.io.X_log) {
@@ -432,7 +434,7 @@ __global__ void __launch_bounds__(128, UVS_BD_MINB) bd_closed_loop_kernel(const 
                         if (a.io.flags_log) a.io.flags_log[bt] = flags | ib_flags | (epoch << UVS_FLAG_EPOCH_SHIFT);
                     }
                 }
-                if (a.io.dq_in && trial_ok) {                            // replay gate: recorded command
+                if (EXTRAS && a.io.dq_in && trial_ok) {                  // replay gate: recorded command
 #pragma unroll
                     for (int r = 0; r < 6; ++r) dq_new[r] = a.io.dq_in[((size_t)b * T + k) * 6 + r];
                 }
@@ -501,7 +503,10 @@ static cudaError_t bd_closed_launch(const ClosedLoopArgs& a, int sms, cudaStream
     constexpr int GPW = 32 / GroupSize<M>::value;
     const long long warps = (a.B + GPW - 1) / GPW;
     const long long need = (warps + 3) / 4;
-    if ((a.cfg.v_max > 0.0) || (a.cfg.a_max > 0.0) || (a.cfg.servo_gain > 0.0 && a.cfg.servo_gain != 1.0))
+    const uvs_closed_loop_io& io = a.io;
+    const bool extras = (a.cfg.v_max > 0.0) || (a.cfg.a_max > 0.0) || (a.cfg.servo_gain > 0.0 && a.cfg.servo_gain != 1.0) ||
+                        io.dq_in || io.X_log || io.P_log || io.dq_log || io.kappa_log || io.flags_log;
+    if (extras)
         bd_closed_loop_kernel<M, METHOD, true><<<(int)bd_grid(bd_closed_loop_kernel<M, METHOD, true>, need, sms), 128, 0, st>>>(a);
     else
         bd_closed_loop_kernel<M, METHOD, false><<<(int)bd_grid(bd_closed_loop_kernel<M, METHOD, false>, need, sms), 128, 0, st>>>(a);

@@ -311,7 +311,7 @@ UVS_DEV void rank_update(PBlock& pb, double* Pd, const double* Kt, const double*
 // latency gaps with update FMAs.  Same results as rank_update() followed by pinv_warp().
 template <int M>
 UVS_DEV void ibvs_with_rank_update(PBlock& pb, double* Pd, const double* Kt, const double* Ut, const double* J,
-                                   double b_lane, double* sc, int lane, double (&x)[6], int& flags, double* big) {
+                                   double b_lane, double* sc, int lane, double (&x)[6], int& flags, double* big UVS_CLK_ARGS) {
     static_assert(M >= 6, "M < 6 uses the J J^T path of pinv_group");
     constexpr int K = 6;
     constexpr int C1 = M / 4, C2 = (3 * M) / 4, C3 = M - 1;      // k ranges handed to the four stages
@@ -339,6 +339,7 @@ UVS_DEV void ibvs_with_rank_update(PBlock& pb, double* Pd, const double* Kt, con
         if (lane < 27) sc[e] = s;                    // sG = sc[0..21), sg = sc[21..27)
     }
     __syncwarp();
+    UVS_CLK(6);
     double L[K * (K + 1) / 2], g[K];
     bool ok;
     {   // stage 2: factor, first solve, residual
@@ -364,6 +365,7 @@ UVS_DEV void ibvs_with_rank_update(PBlock& pb, double* Pd, const double* Kt, con
         if (lane < M) sr[lane] = s;
     }
     __syncwarp();
+    UVS_CLK(7);
     {   // stage 3: J^T r
         const int col = lane < 6 ? lane : 5;
         double s = 0.0;
@@ -373,6 +375,7 @@ UVS_DEV void ibvs_with_rank_update(PBlock& pb, double* Pd, const double* Kt, con
         if (lane < 6) sx[lane] = s;
     }
     __syncwarp();
+    UVS_CLK(8);
     {   // stage 4: refinement solve
         double d[K];
 #pragma unroll
@@ -384,6 +387,7 @@ UVS_DEV void ibvs_with_rank_update(PBlock& pb, double* Pd, const double* Kt, con
         rank_update_diag<M, false>(Pd, Kt, Ut, lane);
     }
     __syncwarp();
+    UVS_CLK(9);
     if (!ok) {
         flags |= UVS_FLAG_RANK_DEFICIENT;
         pinv_fallback_osj<32>(M, J, sb, big, sx, lane);
@@ -643,11 +647,16 @@ struct StepOut {
 template <int M, int METHOD, bool DEFER = false, bool FAST = false>
 UVS_DEV double dense_step(PBlock& pb, DenseWS<M, METHOD == UVS_METHOD_MCKF>& w, const DenseConsts<M>& cc,
                           const uvs_filter_params& fp, const double (&h)[6], double z_lane, double sigma,
+#ifdef UVS_PHASE_CLOCKS
+                          int lane, StepOut& out, double inv_s2 UVS_CLK_ARGS) {
+#else
                           int lane, StepOut& out, double inv_s2 = 0.0) {
+#endif
     constexpr int N = 6 * M, LD = N + 2;
     const bool r_id = FAST || (cc.r_identity != 0);
     const bool joseph = FAST || (fp.joseph != 0);
     predict_and_A<M>(pb, w.Pd, w.At, h, fp.Q, FAST ? 1 : cc.q_identity, lane);
+    UVS_CLK(2);
 
     // innovation nu = Z - H X (lane i < M), published through shared memory
     double nu_l = 0.0;
@@ -695,8 +704,10 @@ UVS_DEV double dense_step(PBlock& pb, DenseWS<M, METHOD == UVS_METHOD_MCKF>& w, 
             d_mode = joseph ? 2 : 0;
         }
         double* ddiag = w.ib + 8;
+        UVS_CLK(3);
         const bool ok = build_and_factor_S<M>(w.At, h, cc, w_lane, plain_R, s0_scale, w.S, w.ib, w.D, ddiag, d_mode,
                                               dscale, L, lane, r_id);
+        UVS_CLK(4);
         if (!ok) {                       // S not SPD: skip the correction, P keeps +Q
             out.flags |= UVS_FLAG_NOT_SPD;
             for (int e = lane; e < M * LD; e += 32) w.Kt[e] = 0.0;
@@ -768,6 +779,7 @@ UVS_DEV double dense_step(PBlock& pb, DenseWS<M, METHOD == UVS_METHOD_MCKF>& w, 
             }
         }
         __syncwarp();
+        UVS_CLK(5);
         if (DEFER) { out.rank_pending = true; return kappa; }
         rank_update<M, false>(pb, w.Pd, w.Kt, w.Ut, lane);
         __syncwarp();

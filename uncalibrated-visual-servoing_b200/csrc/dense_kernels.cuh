@@ -81,7 +81,11 @@ __global__ void UVS_DENSE_BOUNDS dense_replay_kernel(const __grid_constant__ Rep
                 sigma = annealed_bw(a.fp.kernel_bw, a.fp.annealing, k, a.k_max);
             }
             StepOut so;
-            const double kappa = dense_step<M, METHOD>(pb, w, cc, a.fp, h, z, sigma, lane, so);
+#ifdef UVS_PHASE_CLOCKS
+            unsigned long long clk_acc[UVS_NPHASE] = {};
+            long long clk_last = 0;
+#endif
+            const double kappa = dense_step<M, METHOD>(pb, w, cc, a.fp, h, z, sigma, lane, so, 0.0 UVS_CLK_PASS);
             const size_t bt = (size_t)b * a.T + k;
             if (a.X_out) for (int r = lane; r < N; r += 32) a.X_out[bt * N + r] = w.X[r];
             if (a.P_out) store_P<M>(pb, w.Pd, a.P_out + bt * psz, a.p_layout, lane);
@@ -189,7 +193,12 @@ __global__ void UVS_DENSE_BOUNDS dense_closed_loop_kernel(const __grid_constant_
         const bool philox = (a.io.noise_in == nullptr) && (cfg.noise.type != UVS_NOISE_NONE);
         const bool traced = io_traced(a.io);
         double fresh_batch = 0.0;
+#ifdef UVS_PHASE_CLOCKS
+        unsigned long long clk_acc[UVS_NPHASE] = {};
+        long long clk_last = clock64();
+#endif
         for (int k = 0; k < T; ++k) {
+            UVS_CLK(11);
             // ---- plant: joint angles -> this lane's feature coordinate ------------------------------
             // lane j < 6 evaluates sin/cos of DH angle j; lanes < M walk their target point back through
             // the chain into the camera frame (ur10_simulation.py:97-110 + SURVEY Appendix A pixel model)
@@ -219,6 +228,7 @@ __global__ void UVS_DENSE_BOUNDS dense_closed_loop_kernel(const __grid_constant_
                     status = UVS_STATUS_FAIL; flags_all |= UVS_FLAG_OUT_OF_VIEW; break;
                 }
             }
+            UVS_CLK(0);
             double nz = 0.0;
             if (a.io.noise_in) nz = (lane < M) ? a.io.noise_in[((size_t)b * T + k) * M + lane] : 0.0;
             else if (philox) {
@@ -231,6 +241,7 @@ __global__ void UVS_DENSE_BOUNDS dense_closed_loop_kernel(const __grid_constant_
                 const double fresh = shfl_d(fresh_batch, slot * M + (lane % M));
                 nz = next_noise_prefetched(hs, cfg.noise.hold_cnt, fresh, lane, M);
             }
+            UVS_CLK(1);
             const double f_new = f_true + nz;                            // experiment.py:130-135
             const double z = f_new - f_l;                                // experiment.py:170-177
             f_l = f_new;
@@ -242,7 +253,7 @@ __global__ void UVS_DENSE_BOUNDS dense_closed_loop_kernel(const __grid_constant_
             {
                 double h[6];                                             // experiment.py:183-188: the previous
                 load6(w.dq, h);                                          // command (zeros on the first frame)
-                kappa = dense_step<M, METHOD, (M >= 6 && !MCKF), FAST>(pb, w, cc, cfg.filt, h, z, sigma, lane, so, inv_s2);
+                kappa = dense_step<M, METHOD, (M >= 6 && !MCKF), FAST>(pb, w, cc, cfg.filt, h, z, sigma, lane, so, inv_s2 UVS_CLK_PASS);
             }
             flags_all |= so.flags;
             if (so.flags & kAbortFlags) { status = UVS_STATUS_FAIL; break; }      // the reference ends FAIL here (common.cuh)
@@ -252,13 +263,14 @@ __global__ void UVS_DENSE_BOUNDS dense_closed_loop_kernel(const __grid_constant_
             int ib_flags = 0;
             if constexpr (M >= 6 && !MCKF) {
                 if (so.rank_pending)
-                    ibvs_with_rank_update<M>(pb, w.Pd, w.Kt, w.Ut, w.X, kappa * (f_l - desired), w.ib, lane, x, ib_flags, w.jacobi_scratch());
+                    ibvs_with_rank_update<M>(pb, w.Pd, w.Kt, w.Ut, w.X, kappa * (f_l - desired), w.ib, lane, x, ib_flags, w.jacobi_scratch() UVS_CLK_PASS);
                 else
                     pinv_warp<M>(w.X, kappa * (f_l - desired), w.ib, lane, x, ib_flags, w.jacobi_scratch());
             } else {
                 pinv_warp<M>(w.X, kappa * (f_l - desired), w.ib, lane, x, ib_flags, w.jacobi_scratch());
             }
             flags_all |= ib_flags;
+            UVS_CLK(10);
             double dq_l = 0.0;
 #pragma unroll
             for (int r = 0; r < 6; ++r)
@@ -291,6 +303,10 @@ __global__ void UVS_DENSE_BOUNDS dense_closed_loop_kernel(const __grid_constant_
             }
             __syncwarp();
         }
+#ifdef UVS_PHASE_CLOCKS
+        if (lane == 0)
+            for (int i = 0; i < UVS_NPHASE; ++i) atomicAdd(a.phase_clk + i, clk_acc[i]);
+#endif
         // ||.||_2 over the M coordinates
         double s0 = ise * ise, s1 = iae * iae, s2 = itae * itae;
 #pragma unroll

@@ -24,6 +24,9 @@ struct ClosedLoopArgs {
     uvs_closed_loop_io io;
     unsigned long long trial0;
     long long B;
+#ifdef UVS_PHASE_CLOCKS
+    unsigned long long* phase_clk;     // profiling build: device array of UVS_NPHASE totals
+#endif
 };
 
 // noise of this frame for coordinate `lane` with the pair hold of noise.py:81-118

@@ -119,6 +119,7 @@ static __device__ __noinline__ void pinv_fallback_osj(int MM, const double* J, c
         for (int p = 0; p < C - 1; ++p)
             for (int q = p + 1; q < C; ++q) {
                 double alpha = 0.0, beta = 0.0, gamma = 0.0;          // every lane: the same values (uniform control flow)
+#pragma unroll 1
                 for (int r = 0; r < R; ++r) {
                     const double ap = A[r * C + p], aq = A[r * C + q];
                     alpha += ap * ap; beta += aq * aq; gamma += ap * aq;
@@ -129,6 +130,7 @@ static __device__ __noinline__ void pinv_fallback_osj(int MM, const double* J, c
                 const double t = copysign(1.0, zeta) / (fabs(zeta) + sqrt(zeta * zeta + 1.0));
                 const double c = rsqrt(t * t + 1.0), sn = t * c;
                 __syncwarp(mask);                                     // all lanes have read columns p, q
+#pragma unroll 1
                 for (int i = gl; i < R + C; i += GS) {                // rows of A, then rows of V
                     double* row = (i < R) ? A + i * C : V + (i - R) * C;
                     const double vp = row[p], vq = row[q];
@@ -139,34 +141,30 @@ static __device__ __noinline__ void pinv_fallback_osj(int MM, const double* J, c
             }
         if (!rotated) break;
     }
-    // squared singular values, cutoff (numpy: s > rcond * s_max with rcond = 1e-15), projections.  Constant trip counts
-    // with a predicate keep s2 / proj in registers (statically indexed).
-    double s2[6], smax2 = 0.0;
-#pragma unroll
-    for (int c = 0; c < 6; ++c) {
+    // squared singular values, cutoff (numpy: s > rcond * s_max with rcond = 1e-15), projections.  Written with rolled
+    // loops and NO local arrays: the register footprint of this noinline function is what its callers have to spill
+    // around the call (measured: 70 registers here cost the block-diagonal closed loop 8-15 % of its throughput).
+    double smax2 = 0.0;
+    for (int c = 0; c < C; ++c) {
         double a = 0.0;
-        if (c < C) for (int r = 0; r < R; ++r) a += A[r * C + c] * A[r * C + c];
-        s2[c] = a;
+        for (int r = 0; r < R; ++r) a += A[r * C + c] * A[r * C + c];
         smax2 = fmax(smax2, a);
     }
-    double proj[6];
-#pragma unroll
-    for (int c = 0; c < 6; ++c) {
-        double t = 0.0;
-        if (c < C && sqrt(s2[c]) > 1e-15 * sqrt(smax2) && smax2 > 0.0) {
-            if (tall) { for (int r = 0; r < R; ++r) t += A[r * C + c] * b[r]; }
-            else      { for (int k = 0; k < C; ++k) t += V[k * C + c] * b[k]; }
-            t /= s2[c];
-        }
-        proj[c] = t;
-    }
     __syncwarp(mask);
-    for (int i = gl; i < 6; i += GS) {                    // groups narrower than 6 lanes (GS = 2) take several components
-        double y = 0.0;
-#pragma unroll
-        for (int c = 0; c < 6; ++c)
-            if (c < C) y += (tall ? V[i * C + c] : A[i * C + c]) * proj[c];
-        x_out[i] = y;
+    for (int i = gl; i < 6; i += GS) x_out[i] = 0.0;     // groups narrower than 6 lanes (GS = 2) own several components
+    const double cut = 1e-15 * sqrt(smax2);
+    for (int c = 0; c < C; ++c) {
+        double s2 = 0.0, t = 0.0;
+        for (int r = 0; r < R; ++r) s2 += A[r * C + c] * A[r * C + c];
+        if (sqrt(s2) > cut && smax2 > 0.0) {                         // uniform in the group
+            if (tall) {
+                for (int r = 0; r < R; ++r) t += A[r * C + c] * b[r];
+            } else {
+                for (int k = 0; k < C; ++k) t += V[k * C + c] * b[k];
+            }
+            t /= s2;
+            for (int i = gl; i < 6; i += GS) x_out[i] += (tall ? V[i * C + c] : A[i * C + c]) * t;   // each x_out[i] has one owner
+        }
     }
     __syncwarp(mask);
 }

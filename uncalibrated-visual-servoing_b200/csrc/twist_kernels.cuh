@@ -157,6 +157,10 @@ __global__ void __launch_bounds__(kTwistThreads, 2) twist_closed_loop_kernel(con
         const bool servo = (cfg.v_max > 0.0) || (cfg.a_max > 0.0) || (cfg.servo_gain > 0.0 && cfg.servo_gain != 1.0);
         double v_prev[6] = {0, 0, 0, 0, 0, 0};
         const bool traced = io_traced(a.io);
+#ifdef UVS_PHASE_CLOCKS
+        unsigned long long clk_acc[UVS_NPHASE] = {};
+        long long clk_last = 0;
+#endif
 
         for (int k = 0; k < T; ++k) {
             if (tw.err_threshold >= 0.0 && !(sqrt(err2) > tw.err_threshold)) break;     // kalman_4_features.py:111
@@ -231,7 +235,7 @@ __global__ void __launch_bounds__(kTwistThreads, 2) twist_closed_loop_kernel(con
                 load6(w.dq, h);                                            // kalman_4_features.py:152-156
                 const double sigma = annealed_bw(cfg.filt.kernel_bw, cfg.filt.annealing, k, T);
                 StepOut so;
-                kappa = dense_step<M, FILTER, DEFER, FAST>(pb, w, cc, cfg.filt, h, z, sigma, lane, so, 1.0 / (sigma * sigma));
+                kappa = dense_step<M, FILTER, DEFER, FAST>(pb, w, cc, cfg.filt, h, z, sigma, lane, so, 1.0 / (sigma * sigma) UVS_CLK_PASS);
                 flags_all |= so.flags;
                 step_flags = so.flags | (so.epoch << UVS_FLAG_EPOCH_SHIFT);
                 rank_pending = so.rank_pending;
@@ -243,7 +247,7 @@ __global__ void __launch_bounds__(kTwistThreads, 2) twist_closed_loop_kernel(con
             double x[6];
             int ib_flags = 0;
             if constexpr (DEFER) {
-                if (rank_pending) ibvs_with_rank_update<M>(pb, w.Pd, w.Kt, w.Ut, w.X, kappa * e_l, w.ib, lane, x, ib_flags, w.jacobi_scratch());
+                if (rank_pending) ibvs_with_rank_update<M>(pb, w.Pd, w.Kt, w.Ut, w.X, kappa * e_l, w.ib, lane, x, ib_flags, w.jacobi_scratch() UVS_CLK_PASS);
                 else pinv_warp<M>(w.X, kappa * e_l, w.ib, lane, x, ib_flags, w.jacobi_scratch());
             } else {
                 pinv_warp<M>(w.X, kappa * e_l, w.ib, lane, x, ib_flags, w.jacobi_scratch());
