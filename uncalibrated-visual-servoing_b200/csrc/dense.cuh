@@ -390,7 +390,9 @@ UVS_DEV void ibvs_with_rank_update(PBlock& pb, double* Pd, const double* Kt, con
     UVS_CLK(9);
     if (!ok) {
         flags |= UVS_FLAG_RANK_DEFICIENT;
-        pinv_fallback_osj<32>(M, J, sb, big, sx, lane);
+        int mm = M;
+        asm volatile("" : "+r"(mm));       // see pinv_group
+        pinv_fallback_osj<32>(mm, J, sb, big, sx, lane);
     }
     __syncwarp();
     if (!ok) {

@@ -297,7 +297,9 @@ UVS_DEV void pinv_group(const double* J, double b_lane, double* sc, int gl, doub
     __syncwarp();
     if (!ok) {
         flags |= UVS_FLAG_RANK_DEFICIENT;
-        pinv_fallback_osj<GS>(M, J, sb, (M >= 6) ? big : sG, sx, gl);      // M < 6: sG (21 doubles) is unused, A + V need 6 M + M^2
+        int mm = M;
+        asm volatile("" : "+r"(mm));       // opaque: keeps the compiler from cloning the noinline fallback per constant M
+        pinv_fallback_osj<GS>(mm, J, sb, (M >= 6) ? big : sG, sx, gl);     // M < 6: sG (21 doubles) is unused, A + V need 6 M + M^2
     }
     __syncwarp();
     if (!ok) {
