@@ -60,7 +60,7 @@ struct alignas(16) DenseWS {
     static_assert(2 * M * M >= pinv_scratch_doubles(M), "S + D hold the work matrices of pinv_fallback_osj");
     double ib[56];                              // weights / IBVS scratch (G 21, g 6, b 8, res 8, x 6)
     double nu[M + (M & 1)];                     // innovation, read back by every lane
-    double Lc[M * (M + 1) / 2 + ((M * (M + 1) / 2) & 1)];   // chol(S), packed lower, reciprocal diagonal
+    double Lc[M * (M + 1) / 2 + ((M * (M + 1) / 2) & 1)];   // S = L D L^T: packed unit-lower factor, reciprocal pivots on the diagonal
     double q[6];                                // closed loop: joint positions, the last command,
     double dq[6];                               // and sin/cos of the DH angles of this frame
     double sc[12];
@@ -350,13 +350,10 @@ UVS_DEV void ibvs_with_rank_update(PBlock& pb, double* Pd, const double* Kt, con
         double gsum = 0.0;
 #pragma unroll
         for (int i = 0; i < K; ++i) gsum += L[tri(i, i)];
-        ok = chol_packed<K>(L);
+        ok = ldl_packed<K>(L);
 #pragma unroll
-        for (int j = 0; j < K; ++j) {
-            const double inv = L[tri(j, j)];
-            ok = ok && (inv * inv * gsum * kPinvPivotTol < 1.0);
-        }
-        chol_solve<K>(L, g);
+        for (int j = 0; j < K; ++j) ok = ok && (L[tri(j, j)] * gsum * kPinvPivotTol < 1.0);    // L[j][j] = 1 / pivot
+        ldl_solve<K>(L, g);
         const int row = lane < M ? lane : M - 1;
         double s = sb[row];
 #pragma unroll
@@ -380,9 +377,11 @@ UVS_DEV void ibvs_with_rank_update(PBlock& pb, double* Pd, const double* Kt, con
         double d[K];
 #pragma unroll
         for (int i = 0; i < K; ++i) d[i] = sx[i];
-        chol_solve<K>(L, d);
+        ldl_solve<K>(L, d);
+        double dn2 = 0.0, xn2 = 0.0;
 #pragma unroll
-        for (int i = 0; i < 6; ++i) x[i] = g[i] + d[i];
+        for (int i = 0; i < 6; ++i) { x[i] = g[i] + d[i]; dn2 += d[i] * d[i]; xn2 += x[i] * x[i]; }
+        ok = ok && (dn2 <= kPinvRefineTol2 * xn2);        // a posteriori conditioning test, see smallmat.cuh
         rank_update_offdiag<M, false, C3, M>(pb, Kt, Ut);
         rank_update_diag<M, false>(Pd, Kt, Ut, lane);
     }
@@ -592,45 +591,40 @@ UVS_DEV bool build_and_factor_S(const double* Ain, const double (&h)[6], const D
 #pragma unroll
         for (int j = 0; j < M; ++j)
             if (j <= i) L[tri(i, j)] = Ssm[i * M + j];
-    return chol_packed<M>(L);
+    return ldl_packed<M>(L);          // unit lower factor, reciprocal pivots on the diagonal
 }
 
-// x_r <- (L L^T)^-1 x_r for R right-hand sides at once, with L (packed lower, reciprocal diagonal) read from
-// shared memory: every access is a warp-wide broadcast with a compile-time offset, so L costs no registers in
-// the gain phase, and the R substitutions are independent dependency chains the scheduler can interleave.
+// x_r <- (L D L^T)^-1 x_r for R right-hand sides at once, with the factor (ldl_packed layout: unit lower, reciprocal
+// pivots on the diagonal) read from shared memory: every access is a warp-wide broadcast with a compile-time offset, so
+// the factor costs no registers in the gain phase, and the R substitutions are independent dependency chains the
+// scheduler can interleave.  Unit diagonal: one FMA per substitution step on the critical path.
 template <int M, int R>
-UVS_DEV void chol_solve_sm(const double* Ls, double (&x)[R][M]) {
+UVS_DEV void ldl_solve_sm(const double* Ls, double (&x)[R][M]) {
 #pragma unroll
     for (int j = 0; j < M; ++j) {
-        double s[R];
-#pragma unroll
-        for (int r = 0; r < R; ++r) s[r] = x[r][j];
 #pragma unroll
         for (int k = 0; k < M; ++k)
             if (k < j) {
                 const double l = Ls[tri(j, k)];
 #pragma unroll
-                for (int r = 0; r < R; ++r) s[r] -= l * x[r][k];
+                for (int r = 0; r < R; ++r) x[r][j] -= l * x[r][k];
             }
+    }
+#pragma unroll
+    for (int j = 0; j < M; ++j) {
         const double d = Ls[tri(j, j)];
 #pragma unroll
-        for (int r = 0; r < R; ++r) x[r][j] = s[r] * d;
+        for (int r = 0; r < R; ++r) x[r][j] *= d;
     }
 #pragma unroll
     for (int j = M - 1; j >= 0; --j) {
-        double s[R];
-#pragma unroll
-        for (int r = 0; r < R; ++r) s[r] = x[r][j];
 #pragma unroll
         for (int k = 0; k < M; ++k)
             if (k > j) {
                 const double l = Ls[tri(k, j)];
 #pragma unroll
-                for (int r = 0; r < R; ++r) s[r] -= l * x[r][k];
+                for (int r = 0; r < R; ++r) x[r][j] -= l * x[r][k];
             }
-        const double d = Ls[tri(j, j)];
-#pragma unroll
-        for (int r = 0; r < R; ++r) x[r][j] = s[r] * d;
     }
 }
 
@@ -748,11 +742,11 @@ UVS_DEV double dense_step(PBlock& pb, DenseWS<M, METHOD == UVS_METHOD_MCKF>& w, 
             {
                 const double* Ls = w.Lc;
                 asm volatile("" : "+l"(Ls));                      // keep the loads inside the block (no hoisting into registers)
-                chol_solve_sm<M, RPL>(Ls, x);
+                ldl_solve_sm<M, RPL>(Ls, x);
             }
 #else
 #pragma unroll
-            for (int j = 0; j < RPL; ++j) chol_solve<M>(L, x[j]);  // Kp row = A row S^-1
+            for (int j = 0; j < RPL; ++j) ldl_solve<M>(L, x[j]);   // Kp row = A row S^-1
 #endif
 #pragma unroll
             for (int j = 0; j < RPL; ++j) {
@@ -856,7 +850,7 @@ UVS_DEV double dense_step(PBlock& pb, DenseWS<M, METHOD == UVS_METHOD_MCKF>& w, 
                 double x[M];
 #pragma unroll
                 for (int k = 0; k < M; ++k) x[k] = Ain[k * LD + row];
-                chol_solve<M>(L, x);
+                ldl_solve<M>(L, x);
                 double xc = w.X[row];
 #pragma unroll
                 for (int k = 0; k < M; ++k) { w.Kt[k * LD + row] = x[k]; xc += x[k] * nu[k]; }

@@ -275,9 +275,11 @@ __global__ void UVS_DENSE_BOUNDS dense_closed_loop_kernel(const __grid_constant_
 #pragma unroll
             for (int r = 0; r < 6; ++r)
                 if (lane == r) dq_l = -cfg.ibvs_gain * x[r];
-            bool bad = !isfinite(dq_l);
-            for (int r = lane; r < N; r += 32) bad = bad || !isfinite(w.X[r]);
-            if (__any_sync(UVS_FULL_MASK, bad)) {                        // experiment.py:313-316
+            // np.linalg.pinv raises on a non-finite Jacobian (experiment.py:313-316).  Testing the command is enough: a NaN or
+            // Inf anywhere in X = J poisons every entry of the Gram matrix J^T J (each sums over all rows), so the
+            // factorisation is rejected, the rank-revealing path returns NaN and dq is non-finite; no scan of X needed.
+            const bool bad = !isfinite(dq_l);
+            if (__any_sync(UVS_FULL_MASK, bad)) {
                 status = UVS_STATUS_FAIL; flags_all |= UVS_FLAG_NONFINITE; break;
             }
             // logging (experiment.py:323-331) and error integrals (plot_errorbar.m:39-84)

@@ -9,7 +9,12 @@
 namespace uvs {
 
 // hand-over from the Cholesky path of the pseudo-inverse to the rank-revealing one: pivot <= kPinvPivotTol * trace(Gram)
-constexpr double kPinvPivotTol = 1e-10;
+constexpr double kPinvPivotTol = 1e-11;
+// ... and a posteriori: the refinement step's correction measures the error of the first normal-equations solve
+// (~ eps cond^2); the refined result is good to about its square.  Corrections above 3e-5 of the solution (cond >~ 4e5)
+// go to the rank-revealing path too.  (A pivot test alone underestimates cond(J) whenever the weakest singular vector
+// has little weight on the last-eliminated coordinate: measured 2e-6 errors at cond = 1e7.)
+constexpr double kPinvRefineTol2 = 3e-5 * 3e-5;
 
 // packed lower-triangular index
 __host__ __device__ constexpr int tri(int i, int j) { return i * (i + 1) / 2 + j; }
@@ -71,6 +76,76 @@ UVS_DEV void chol_solve(const double (&L)[M * (M + 1) / 2], double (&x)[M]) {
 #pragma unroll
         for (int k = 0; k < M; ++k) if (k > j) s -= L[tri(k, j)] * x[k];
         x[j] = s * L[tri(j, j)];
+    }
+}
+
+// 1/d for finite normal d: MUFU.RCP64H seed + two Newton steps (~1 ulp), no special-case handling (callers test the pivot).
+UVS_DEV double fast_rcp(double d) {
+    double y;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(d));
+    double t = fma(-d, y, 1.0);
+    y = fma(y, t, y);
+    t = fma(-d, y, 1.0);
+    y = fma(y, t, y);
+    return y;
+}
+
+// In-place square-root-free factorisation A = L D L^T of a packed lower SPD matrix held in registers.  On exit the strictly
+// lower entries hold the UNIT lower factor and the diagonal holds 1 / d_j.  Same pivots d_j as the Cholesky factorisation
+// (d_j = l_jj^2), so the same positivity test; returns false when a pivot is not positive / finite.
+// Why not Cholesky: the factorisations of S (M x M) and of the Gram matrix (6 x 6) are redundant per lane and sit on the
+// frame's critical path.  Per column the dependent chain is pivot -> reciprocal (MUFU + 4 FMA instead of rsqrt's MUFU + 6)
+// -> scale, and every substitution step of the solves loses its multiplication by the reciprocal diagonal (unit
+// diagonal: one FMA per step instead of FMA + MUL) — ~600 dependent cycles per filter-step (tools/phase_clocks.py).
+// The last column's UNSCALED entries u_i = l_ij d_j are kept so that the next pivot's last term does not wait for a
+// scale-then-rescale round trip.
+template <int M>
+UVS_DEV bool ldl_packed(double (&L)[M * (M + 1) / 2]) {
+    bool ok = true;
+    double dd[M], u[M];
+#pragma unroll
+    for (int j = 0; j < M; ++j) {
+        double w[M];                                   // row j of L D: w_k = l_jk d_k
+#pragma unroll
+        for (int k = 0; k < M; ++k)
+            if (k < j) w[k] = (k == j - 1) ? u[j] : L[tri(j, k)] * dd[k];
+        double d = L[tri(j, j)];
+#pragma unroll
+        for (int k = 0; k < M; ++k) if (k < j) d -= L[tri(j, k)] * w[k];
+        ok = ok && (d > 0.0) && isfinite(d);
+        dd[j] = d;
+        const double inv = fast_rcp(d);
+        L[tri(j, j)] = inv;
+#pragma unroll
+        for (int i = 0; i < M; ++i) if (i > j) {
+            double s = L[tri(i, j)];
+#pragma unroll
+            for (int k = 0; k < M; ++k) if (k < j) s -= L[tri(i, k)] * w[k];
+            u[i] = s;
+            L[tri(i, j)] = s * inv;
+        }
+    }
+    return ok;
+}
+
+// x <- (L D L^T)^-1 x   with L from ldl_packed (unit lower, reciprocal pivots on the diagonal)
+template <int M>
+UVS_DEV void ldl_solve(const double (&L)[M * (M + 1) / 2], double (&x)[M]) {
+#pragma unroll
+    for (int j = 0; j < M; ++j) {
+        double s = x[j];
+#pragma unroll
+        for (int k = 0; k < M; ++k) if (k < j) s -= L[tri(j, k)] * x[k];
+        x[j] = s;
+    }
+#pragma unroll
+    for (int j = 0; j < M; ++j) x[j] *= L[tri(j, j)];
+#pragma unroll
+    for (int j = M - 1; j >= 0; --j) {
+        double s = x[j];
+#pragma unroll
+        for (int k = 0; k < M; ++k) if (k > j) s -= L[tri(k, j)] * x[k];
+        x[j] = s;
     }
 }
 
@@ -145,11 +220,14 @@ static __device__ __noinline__ void pinv_fallback_osj(int MM, const double* J, c
     // loops and NO local arrays: the register footprint of this noinline function is what its callers have to spill
     // around the call (measured: 70 registers here cost the block-diagonal closed loop 8-15 % of its throughput).
     double smax2 = 0.0;
+    bool finite = true;                                   // np.linalg.pinv raises on NaN / Inf: hand NaN back (-> trial FAIL)
     for (int c = 0; c < C; ++c) {
         double a = 0.0;
         for (int r = 0; r < R; ++r) a += A[r * C + c] * A[r * C + c];
+        finite = finite && (a < INFINITY);                // false for NaN too
         smax2 = fmax(smax2, a);
     }
+    for (int r = 0; r < MM; ++r) finite = finite && (fabs(b[r]) < INFINITY);
     __syncwarp(mask);
     for (int i = gl; i < 6; i += GS) x_out[i] = 0.0;     // groups narrower than 6 lanes (GS = 2) own several components
     const double cut = 1e-15 * sqrt(smax2);
@@ -167,6 +245,8 @@ static __device__ __noinline__ void pinv_fallback_osj(int MM, const double* J, c
         }
     }
     __syncwarp(mask);
+    if (!finite) for (int i = gl; i < 6; i += GS) x_out[i] = NAN;
+    __syncwarp(mask);
 }
 
 // doubles of per-group shared scratch pinv_fallback_osj needs for an M x 6 Jacobian with M >= 6 (M < 6 fits the group's
@@ -177,10 +257,10 @@ __host__ __device__ constexpr int pinv_scratch_doubles(int M) { return (M >= 6) 
 // (GS = 32: one problem per warp; GS = 8 or 2: several problems per warp, the block-diagonal family).
 // J: [M x 6] row-major in shared memory; b_lane: b_j on group lane j < M; sc: >= 56 doubles of
 // per-group shared scratch; gl = lane index inside the group.  All 32 lanes of the warp must call.
-// Fast path: Cholesky of the smaller Gram matrix (J^T J for M >= 6, J J^T for M < 6) + one step of
+// Fast path: L D L^T of the smaller Gram matrix (J^T J for M >= 6, J J^T for M < 6) + one step of
 // iterative refinement on the residual (corrected semi-normal equations, error ~ eps cond(J)); if a
-// Cholesky pivot is <= 1e-10 trace(Gram) (cond(J) >~ 1e5; the refined normal equations are good to ~(eps cond^2)^2, i.e.
-// 1e-11 there and 2e-6 at cond = 1e7, measured) the group runs pinv_fallback_osj (one-sided Jacobi on J, numpy's 1e-15
+// pivot is <= 1e-11 trace(Gram) (cond(J) >~ 3e5; the refined normal equations are good to ~(eps cond^2)^2, i.e.
+// 4e-10 there and 2e-6 at cond = 1e7, measured) the group runs pinv_fallback_osj (one-sided Jacobi on J, numpy's 1e-15
 // sigma_max cutoff, error ~ eps cond).  Result in x on every lane of the group.  big: pinv_scratch_doubles(M) doubles of
 // per-group shared scratch, required for M >= 6 (M < 6 uses the free head of `sc`).
 template <int M, int GS>
@@ -232,19 +312,16 @@ UVS_DEV void pinv_group(const double* J, double b_lane, double* sc, int gl, doub
     // scale of the rank test: trace(G) (max diag <= trace <= K max diag; a sum is 1 DADD per term where fmax is ~6)
 #pragma unroll
     for (int i = 0; i < K; ++i) gmax += L[tri(i, i)];
-    bool ok = chol_packed<K>(L);
+    bool ok = ldl_packed<K>(L);
 #pragma unroll
-    for (int j = 0; j < K; ++j) {
-        const double inv = L[tri(j, j)];
-        ok = ok && (inv * inv * gmax * kPinvPivotTol < 1.0);
-    }
+    for (int j = 0; j < K; ++j) ok = ok && (L[tri(j, j)] * gmax * kPinvPivotTol < 1.0);        // L[j][j] = 1 / pivot
     // the fast path runs unconditionally (it only touches registers and this group's scratch) so
     // that the warp-wide barriers below are reached by every lane whatever the other groups do
     if (M >= 6) {
         double g[K];
 #pragma unroll
         for (int i = 0; i < K; ++i) g[i] = sg[i];
-        chol_solve<K>(L, g);
+        ldl_solve<K>(L, g);
         if (gl < M) {
             double s = b_lane;
 #pragma unroll
@@ -262,14 +339,16 @@ UVS_DEV void pinv_group(const double* J, double b_lane, double* sc, int gl, doub
         double d[K];
 #pragma unroll
         for (int i = 0; i < K; ++i) d[i] = sx[i];
-        chol_solve<K>(L, d);
+        ldl_solve<K>(L, d);
+        double dn2 = 0.0, xn2 = 0.0;
 #pragma unroll
-        for (int i = 0; i < 6; ++i) x[i] = g[i] + d[i];
+        for (int i = 0; i < 6; ++i) { x[i] = g[i] + d[i]; dn2 += d[i] * d[i]; xn2 += x[i] * x[i]; }
+        ok = ok && (dn2 <= kPinvRefineTol2 * xn2);
     } else {
         double y[K];
 #pragma unroll
         for (int i = 0; i < K; ++i) y[i] = sb[i];
-        chol_solve<K>(L, y);
+        ldl_solve<K>(L, y);
 #pragma unroll
         for (int c = 0; c < 6; ++c) {
             double s = 0.0;
@@ -285,14 +364,17 @@ UVS_DEV void pinv_group(const double* J, double b_lane, double* sc, int gl, doub
             for (int c = 0; c < 6; ++c) s -= J[r * 6 + c] * x[c];
             res[r] = s;
         }
-        chol_solve<K>(L, res);
+        ldl_solve<K>(L, res);
+        double dn2 = 0.0, xn2 = 0.0;
 #pragma unroll
         for (int c = 0; c < 6; ++c) {
             double s = 0.0;
 #pragma unroll
             for (int r = 0; r < M; ++r) s += J[r * 6 + c] * res[r];
             x[c] += s;
+            dn2 += s * s; xn2 += x[c] * x[c];
         }
+        ok = ok && (dn2 <= kPinvRefineTol2 * xn2);
     }
     __syncwarp();
     if (!ok) {
