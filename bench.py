@@ -76,21 +76,22 @@ def parse():
 
 
 def workload_name(mode, trials, total=None, world=1):
-    size = (f"{total} trials per step sharded over {world} GPUs (BASELINE configs[3])" if total is not None and world > 1
+    size = (f"{total} trials per step dealt round-robin to {world} GPUs (BASELINE configs[3])" if total is not None and world > 1
             else f"{trials} trials per GPU per step (BASELINE configs[2])")
     return (f"RMCKF(GMCKF) 4 features / 48 states, closed-loop kinematic UR10 IBVS, alpha-stable noise "
             f"alpha=linspace(1,2,12) beta=0 gamma=1, annealing, kernel_bw=10, T=300 frames, {size}, covariance={mode}")
 
 
 def plan(a, rank, world):
-    """(trials of this rank, first global trial, total trials, scaling) — sweep.shard_range for the strong case."""
+    """(trials of this rank, first global trial, trial stride, total trials, scaling).  Strong case: the trials are dealt
+    round-robin (sweep.shard_interleaved: rank r runs r, r + N, ...) so that every rank has the same mix of noise levels;
+    weak case: a contiguous block per rank."""
     if a.trials is None and (world > 1 or a.total_trials is not None):
         total = a.total_trials or 1_000_000
-        base, extra = divmod(total, world)
-        lo = rank * base + min(rank, extra)
-        return base + (1 if rank < extra else 0), lo, total, "strong"
+        count = (total - rank + world - 1) // world if total > rank else 0
+        return count, rank, world, total, "strong"
     B = a.trials or 100_000
-    return B, rank * B, world * B, "weak"
+    return B, rank * B, 1, world * B, "weak"
 
 
 # ------------------------------------------------------------------------- CPU arm (oracle port)
@@ -184,9 +185,9 @@ def run_reference(a):
     sample = f"{cores} processes x {tpc} closed-loop trials x {T_FRAMES} frames per step (as-written NumPy restatement, OMP_NUM_THREADS=1)"
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": a.gpus, "steps": max(1, a.steps),
-        "warmup": a.warmup, "ms_per_step": float(np.mean(ms)), "higher_is_better": True, "scaling": plan(a, 0, a.gpus)[3],
+        "warmup": a.warmup, "ms_per_step": float(np.mean(ms)), "higher_is_better": True, "scaling": plan(a, 0, a.gpus)[4],
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": workload_name("dense", plan(a, 0, a.gpus)[0], plan(a, 0, a.gpus)[2], a.gpus),
+        "config": {"workload": workload_name("dense", plan(a, 0, a.gpus)[0], plan(a, 0, a.gpus)[3], a.gpus),
                    "trials_per_gpu": plan(a, 0, a.gpus)[0], "frames": T_FRAMES,
                    "sample": f"each step runs {cores * tpc} trials of that workload (bounded CPU sample)",
                    "noise_seed": NOISE_SEED, "pose_seed": POSE_SEED},
@@ -254,7 +255,7 @@ def run_ours(a):
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
-    B, trial0, total_trials, scaling = plan(a, rank, world)   # contiguous trial shard per rank; Philox keyed by global trial id
+    B, trial0, stride, total_trials, scaling = plan(a, rank, world)   # Philox is keyed by the GLOBAL trial id
     n_levels = len(SWEEP)
     epoch = (total_trials + n_levels - 1) // n_levels
 
@@ -264,7 +265,7 @@ def run_ours(a):
         return E.closed_loop_cfg(p, E.noise_params(L.NOISE_ALPHA_STABLE, seed=NOISE_SEED, alpha=1.5, beta=0.0,
                                                    gamma=1.0, delta=0.0),
                                  T=T_FRAMES, dt=DT, ibvs_gain=0.2, q_start=Q_START, desired_f=DESIRED_F,
-                                 pose_seed=POSE_SEED, sweep=SWEEP, sweep_epoch=epoch, sweep_param=2)
+                                 pose_seed=POSE_SEED, sweep=SWEEP, sweep_epoch=epoch, sweep_param=2, trial_stride=stride)
 
     flush = torch.empty(256 * 1024 * 1024 // 8, dtype=torch.float64, device="cuda")   # > 126 MB L2
     # the per-level statistics block of the job: [n_levels,3,3] sums + [n_levels] failure counts in ONE buffer, so
@@ -274,7 +275,7 @@ def run_ours(a):
 
     def step(cfg, out):
         E.closed_loop(cfg, trial0, B, out=out)
-        E.reduce_stats(out["stats"], out["status"], trial0, epoch, n_levels, out=(sums_v, fail_v))
+        E.reduce_stats(out["stats"], out["status"], trial0, epoch, n_levels, out=(sums_v, fail_v), trial_stride=stride)
 
     def timed(mode, steps, warmup):
         cfg = make_cfg(mode)
@@ -297,7 +298,7 @@ def run_ours(a):
             ks[i].record()
             E.closed_loop(cfg, trial0, B, out=out)
             ke[i].record()
-            E.reduce_stats(out["stats"], out["status"], trial0, epoch, n_levels, out=(sums_v, fail_v))
+            E.reduce_stats(out["stats"], out["status"], trial0, epoch, n_levels, out=(sums_v, fail_v), trial_stride=stride)
         if world > 1:
             dist.all_reduce(packed)                       # THE collective: per-level sums of all steps, once
         e1.record()

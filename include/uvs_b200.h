@@ -108,7 +108,10 @@ typedef struct uvs_closed_loop_cfg {
     int32_t sweep_len;       /* number of noise levels (main.py:104-106), 0 = no sweep    */
     int32_t sweep_epoch;     /* trials per noise level (config "epoch"); level = trial / sweep_epoch */
     int32_t sweep_param;     /* 0 none, 1 = rho, 2 = alpha (main.py:123-126)              */
-    int32_t reserved;
+    int32_t trial_stride;    /* entry b of the batch is global trial trial0 + b * trial_stride (0 or 1: contiguous).  Rank r
+                                of G takes trial0 = r, trial_stride = G to get the same mix of noise levels as every other
+                                rank: a frame's cost depends on the level (alpha = 1 and 2 use cheap samplers), so contiguous
+                                shards of a sweep finish at different times (measured: 2.7 % at G = 2)               */
     double dt;               /* config "dt"                                               */
     double ibvs_gain;        /* config "ibvs_gain"                                        */
     double q_start[6];
@@ -271,10 +274,10 @@ int uvs_closed_loop_stream(const uvs_closed_loop_cfg* cfg, uint64_t trial0, int6
 
 /* Per-noise-level sums for results/plot_errorbar.m:87-94: for level c and
  * statistic s in {ISE,IAE,ITAE}: sums[c][s] = {n_ok, sum x, sum x^2} over
- * SUCCESS trials, plus n_fail[c].  level = (trial0+b) / sweep_epoch (clamped).
+ * SUCCESS trials, plus n_fail[c].  level = (trial0 + b * trial_stride) / sweep_epoch (clamped; stride 0 = 1).
  * sums [n_levels,3,3] and n_fail [n_levels] are ACCUMULATED into (zero them
  * first); they are what is all-reduced across GPUs.  1 <= n_levels <= 512. */
-int uvs_reduce_stats(int64_t B, uint64_t trial0, int32_t sweep_epoch, int32_t n_levels,
+int uvs_reduce_stats(int64_t B, uint64_t trial0, int32_t trial_stride, int32_t sweep_epoch, int32_t n_levels,
                      const double* stats, const int32_t* status, double* sums, double* n_fail,
                      void* stream);
 

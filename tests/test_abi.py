@@ -113,4 +113,4 @@ def test_twist_loop_validates_before_touching_the_device(lib):
     assert handle.uvs_closed_loop(C.byref(cfg), 0, 1, C.byref(io), None) == -1 and "fpi_epoch_max" in lib.last_error()
     cfg.filt.fpi_epoch_max, cfg.sweep_len, cfg.sweep_epoch = 10, 12, 0
     assert handle.uvs_closed_loop(C.byref(cfg), 0, 1, C.byref(io), None) == -1 and "sweep_epoch" in lib.last_error()
-    assert handle.uvs_reduce_stats(1, 0, 1, 513, 8, 8, 8, 8, None) == -1 and "n_levels" in lib.last_error()
+    assert handle.uvs_reduce_stats(1, 0, 1, 1, 513, 8, 8, 8, 8, None) == -1 and "n_levels" in lib.last_error()

@@ -15,17 +15,17 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 WORKER = os.path.join(ROOT, "tests", "multi_gpu_worker.py")
 
 
-def _run(world, out, n_trials, mode, port):
+def _run(world, out, n_trials, mode, shard, port):
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr",
-           "127.0.0.1", "--master-port", str(port), WORKER, str(out), str(n_trials), mode]
+           "127.0.0.1", "--master-port", str(port), WORKER, str(out), str(n_trials), mode, shard]
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT)
     assert r.returncode == 0, r.stderr[-2000:]
     with np.load(out) as z:
         return {k: z[k] for k in z.files}
 
 
-@pytest.mark.parametrize("mode,n_trials", [("blockdiag", 96_000), ("dense", 12_000)])
-def test_results_do_not_depend_on_the_number_of_gpus(tmp_path, mode, n_trials):
+@pytest.mark.parametrize("mode,n_trials,shard", [("blockdiag", 96_000, "contiguous"), ("dense", 12_000, "interleaved")])
+def test_results_do_not_depend_on_the_number_of_gpus(tmp_path, mode, n_trials, shard):
     import torch
     if not torch.cuda.is_available():
         pytest.skip("no CUDA device")
@@ -33,7 +33,7 @@ def test_results_do_not_depend_on_the_number_of_gpus(tmp_path, mode, n_trials):
     worlds = [1, 2] + [g for g in (4, 8) if g <= ndev]
     res = {}
     for i, g in enumerate(worlds):
-        res[g] = _run(g, tmp_path / f"g{g}.npz", n_trials, mode, 29610 + 7 * i + (0 if mode == "dense" else 40))
+        res[g] = _run(g, tmp_path / f"g{g}.npz", n_trials, mode, shard, 29610 + 7 * i + (0 if mode == "dense" else 40))
     base = res[1]
     assert base["stats"].shape == (n_trials, 3) and (base["status"] == 0).mean() > 0.5
     for g in worlds[1:]:

@@ -210,13 +210,14 @@ def test_bench_plan_shards_like_the_driver():
     bench = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(bench)
     a = argparse.Namespace(trials=None, total_trials=None)
-    assert bench.plan(a, 0, 1) == (100_000, 0, 100_000, "weak")
+    assert bench.plan(a, 0, 1) == (100_000, 0, 1, 100_000, "weak")
     for world in (2, 4, 8, 3):
         got = [bench.plan(a, r, world) for r in range(world)]
-        assert all(g[3] == "strong" and g[2] == 1_000_000 for g in got)
-        assert [(g[1], g[1] + g[0]) for g in got] == [sweep.shard_range(1_000_000, r, world) for r in range(world)]
-        assert sum(g[0] for g in got) == 1_000_000
+        assert all(g[4] == "strong" and g[3] == 1_000_000 and g[2] == world for g in got)
+        assert [(g[1], g[2], g[0]) for g in got] == [sweep.shard_interleaved(1_000_000, r, world) for r in range(world)]
+        ids = np.concatenate([g[1] + g[2] * np.arange(g[0]) for g in got])
+        assert len(ids) == 1_000_000 and len(np.unique(ids)) == 1_000_000 and ids.max() == 999_999     # a partition
     a = argparse.Namespace(trials=5000, total_trials=None)
-    assert bench.plan(a, 3, 4) == (5000, 15000, 20000, "weak")
+    assert bench.plan(a, 3, 4) == (5000, 15000, 1, 20000, "weak")
     a = argparse.Namespace(trials=None, total_trials=96_000)
-    assert bench.plan(a, 0, 1) == (96_000, 0, 96_000, "strong")
+    assert bench.plan(a, 0, 1) == (96_000, 0, 1, 96_000, "strong")

@@ -42,7 +42,7 @@ class NoiseParams(C.Structure):
 class ClosedLoopCfg(C.Structure):
     _fields_ = [("filt", FilterParams), ("noise", NoiseParams), ("T", C.c_int32), ("initial_guess", C.c_int32),
                 ("change_q_start", C.c_int32), ("fov_check", C.c_int32), ("sweep_len", C.c_int32),
-                ("sweep_epoch", C.c_int32), ("sweep_param", C.c_int32), ("reserved", C.c_int32),
+                ("sweep_epoch", C.c_int32), ("sweep_param", C.c_int32), ("trial_stride", C.c_int32),
                 ("dt", C.c_double), ("ibvs_gain", C.c_double), ("q_start", C.c_double * 6),
                 ("desired_f", C.c_double * 8), ("targets", C.c_double * 12), ("pose_seed", C.c_uint64),
                 ("sweep", C.c_double * UVS_MAX_SWEEP), ("P0", _dp), ("v_max", C.c_double), ("a_max", C.c_double), ("servo_gain", C.c_double)]
@@ -87,7 +87,7 @@ _PROTOTYPES = {
                               C.POINTER(C.c_int32), C.POINTER(C.c_int32)], C.c_int),
     "uvs_closed_loop_stream": ([C.POINTER(ClosedLoopCfg), C.c_uint64, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p,
                                 C.POINTER(C.c_double), C.POINTER(C.c_double)], C.c_int),
-    "uvs_reduce_stats": ([C.c_int64, C.c_uint64, C.c_int32, C.c_int32, _dp, _dp, _dp, _dp, _dp], C.c_int),
+    "uvs_reduce_stats": ([C.c_int64, C.c_uint64, C.c_int32, C.c_int32, C.c_int32, _dp, _dp, _dp, _dp, _dp], C.c_int),
     "uvs_fp64_peak": ([C.c_int32, C.POINTER(C.c_double), C.POINTER(C.c_double)], C.c_int),
 }
 

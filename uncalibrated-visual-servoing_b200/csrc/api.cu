@@ -118,6 +118,7 @@ static int check_loop_cfg(const uvs_closed_loop_cfg& c) {
     if (c.sweep_len < 0 || c.sweep_len > UVS_MAX_SWEEP) return set_error(UVS_ERR_INVALID, "sweep_len");
     if (c.sweep_param < 0 || c.sweep_param > 2) return set_error(UVS_ERR_INVALID, "sweep_param must be 0, 1 or 2 (got %d)", c.sweep_param);
     if (c.sweep_len > 0 && c.sweep_epoch < 1) return set_error(UVS_ERR_INVALID, "sweep_epoch must be >= 1 (got %d)", c.sweep_epoch);
+    if (c.trial_stride < 0) return set_error(UVS_ERR_INVALID, "trial_stride must be >= 0 (got %d)", c.trial_stride);
     if (!(c.v_max >= 0.0) || !(c.a_max >= 0.0) || !(c.servo_gain >= 0.0))
         return set_error(UVS_ERR_INVALID, "v_max / a_max / servo_gain must be >= 0");
     return 0;
@@ -438,13 +439,14 @@ int uvs_closed_loop_stream(const uvs_closed_loop_cfg* cfg, uint64_t trial0, int6
     return rc;
 }
 
-int uvs_reduce_stats(int64_t B, uint64_t trial0, int32_t sweep_epoch, int32_t n_levels,
+int uvs_reduce_stats(int64_t B, uint64_t trial0, int32_t trial_stride, int32_t sweep_epoch, int32_t n_levels,
                      const double* stats, const int32_t* status, double* sums, double* n_fail, void* stream) {
     // n_levels * 80 B of shared memory per CTA: 512 levels stay under the 48 KB a kernel gets without opting in
     if (!sums || !n_fail || B < 0 || n_levels < 1 || n_levels > 512 || (B > 0 && (!stats || !status)))
         return set_error(UVS_ERR_INVALID, "uvs_reduce_stats: bad argument (1 <= n_levels <= 512)");
     if (B == 0) return 0;
-    return check_cuda(launch_reduce_stats(B, trial0, sweep_epoch, n_levels, stats, status, sums, n_fail,
+    if (trial_stride < 0) return set_error(UVS_ERR_INVALID, "uvs_reduce_stats: trial_stride < 0");
+    return check_cuda(launch_reduce_stats(B, trial0, trial_stride, sweep_epoch, n_levels, stats, status, sums, n_fail,
                                           (cudaStream_t)stream), "reduce_stats");
 }
 

@@ -181,13 +181,13 @@ cudaError_t launch_start_poses(const double* q_start_host, unsigned long long po
 }
 
 // ---- per-level sums for mean / std (plot_errorbar.m:87-94) ----------------------------------------
-__global__ void reduce_stats_kernel(long long B, unsigned long long trial0, int sweep_epoch, int n_levels,
+__global__ void reduce_stats_kernel(long long B, unsigned long long trial0, int trial_stride, int sweep_epoch, int n_levels,
                                     const double* stats, const int32_t* status, double* sums, double* n_fail) {
     extern __shared__ double sh[];                 // [n_levels][10] : 3 x {n, sx, sxx} + n_fail
     for (int i = threadIdx.x; i < n_levels * 10; i += blockDim.x) sh[i] = 0.0;
     __syncthreads();
     for (long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x; b < B; b += (long long)gridDim.x * blockDim.x) {
-        long long lvl = sweep_epoch > 0 ? (long long)((trial0 + (uint64_t)b) / (uint64_t)sweep_epoch) : 0;
+        long long lvl = sweep_epoch > 0 ? (long long)((trial0 + (uint64_t)b * (uint64_t)trial_stride) / (uint64_t)sweep_epoch) : 0;
         if (lvl >= n_levels) lvl = n_levels - 1;
         double* s = sh + lvl * 10;
         if (status[b] == UVS_STATUS_SUCCESS) {
@@ -211,13 +211,13 @@ __global__ void reduce_stats_kernel(long long B, unsigned long long trial0, int 
     }
 }
 
-cudaError_t launch_reduce_stats(long long B, unsigned long long trial0, int sweep_epoch, int n_levels,
+cudaError_t launch_reduce_stats(long long B, unsigned long long trial0, int trial_stride, int sweep_epoch, int n_levels,
                                 const double* stats, const int32_t* status, double* sums, double* n_fail,
                                 cudaStream_t st) {
     int grid = (int)((B + 255) / 256);
     if (grid > 592) grid = 592;
     if (grid < 1) grid = 1;
-    reduce_stats_kernel<<<grid, 256, n_levels * 10 * sizeof(double), st>>>(B, trial0, sweep_epoch, n_levels, stats,
+    reduce_stats_kernel<<<grid, 256, n_levels * 10 * sizeof(double), st>>>(B, trial0, trial_stride > 1 ? trial_stride : 1, sweep_epoch, n_levels, stats,
                                                                            status, sums, n_fail);
     return cudaGetLastError();
 }

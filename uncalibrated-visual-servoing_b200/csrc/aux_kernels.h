@@ -14,7 +14,7 @@ cudaError_t launch_noise_fill(const uvs_noise_params& np, unsigned long long tri
                               double* out, cudaStream_t st);
 cudaError_t launch_start_poses(const double* q_start_host, unsigned long long pose_seed, int change,
                                unsigned long long trial0, long long B, double* q_out, cudaStream_t st);
-cudaError_t launch_reduce_stats(long long B, unsigned long long trial0, int sweep_epoch, int n_levels,
+cudaError_t launch_reduce_stats(long long B, unsigned long long trial0, int trial_stride, int sweep_epoch, int n_levels,
                                 const double* stats, const int32_t* status, double* sums, double* n_fail,
                                 cudaStream_t st);
 cudaError_t run_fp64_peak(int iters, int sm_count, double* tflops, double* ms_out);

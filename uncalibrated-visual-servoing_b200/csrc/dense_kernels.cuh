@@ -126,7 +126,7 @@ __global__ void UVS_DENSE_BOUNDS dense_closed_loop_kernel(const __grid_constant_
     DenseWS<M, MCKF>& w = wsv[warp];
 
     for (long long b = (long long)blockIdx.x * wpc + warp; b < a.B; b += (long long)gridDim.x * wpc) {
-        const uint64_t trial = a.trial0 + (uint64_t)b;
+        const uint64_t trial = a.trial0 + (uint64_t)b * (uint64_t)(cfg.trial_stride > 1 ? cfg.trial_stride : 1);
         // noise level of this trial (main.py:121-127)
         double rho = cfg.noise.rho, alpha = cfg.noise.alpha;
         if (cfg.sweep_len > 0 && cfg.sweep_param != 0) {

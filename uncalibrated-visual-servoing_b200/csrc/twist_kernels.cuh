@@ -98,7 +98,7 @@ __global__ void __launch_bounds__(kTwistThreads, 2) twist_closed_loop_kernel(con
     const int T = cfg.T;
 
     for (long long b = (long long)blockIdx.x * wpc + warp; b < a.B; b += (long long)gridDim.x * wpc) {
-        const uint64_t trial = a.trial0 + (uint64_t)b;
+        const uint64_t trial = a.trial0 + (uint64_t)b * (uint64_t)(cfg.trial_stride > 1 ? cfg.trial_stride : 1);
         double rho = cfg.noise.rho, alpha = cfg.noise.alpha;
         if (cfg.sweep_len > 0 && cfg.sweep_param != 0) {                 // main.py:121-127
             long long lvl = (long long)(trial / (uint64_t)(cfg.sweep_epoch > 0 ? cfg.sweep_epoch : 1));

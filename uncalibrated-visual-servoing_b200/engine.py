@@ -167,7 +167,7 @@ def start_poses(q_start, pose_seed, change_q_start, trial0, B, device="cuda"):
 
 def closed_loop_cfg(filt, noise, *, T, dt, ibvs_gain, q_start, desired_f, targets=None, initial_guess=True,
                     change_q_start=True, fov_check=False, pose_seed=12345, sweep=None, sweep_epoch=1,
-                    sweep_param=0, P0=None, v_max=0.0, a_max=0.0, servo_gain=0.0):
+                    sweep_param=0, P0=None, v_max=0.0, a_max=0.0, servo_gain=0.0, trial_stride=1):
     cfg = L.ClosedLoopCfg()
     cfg.filt = filt
     cfg.noise = noise
@@ -177,6 +177,7 @@ def closed_loop_cfg(filt, noise, *, T, dt, ibvs_gain, q_start, desired_f, target
     if len(sweep) > L.UVS_MAX_SWEEP:
         raise ValueError("sweep too long")
     cfg.sweep_len, cfg.sweep_epoch, cfg.sweep_param = len(sweep), int(sweep_epoch), int(sweep_param)
+    cfg.trial_stride = int(trial_stride)        # batch entry b = global trial trial0 + b * trial_stride (interleaved shards)
     for i, v in enumerate(sweep):
         cfg.sweep[i] = v
     cfg.dt, cfg.ibvs_gain = float(dt), float(ibvs_gain)
@@ -328,7 +329,7 @@ def closed_loop_stream(cfg, trial0, B, chunk=4096, sink=None):
     return dict(d2h_gbs=gbs.value, wall_s=wall.value)
 
 
-def reduce_stats(stats, status, trial0, sweep_epoch, n_levels, out=None):
+def reduce_stats(stats, status, trial0, sweep_epoch, n_levels, out=None, trial_stride=1):
     """Per-level sums [n_levels,3,3] = {n_ok, sum, sum of squares} and n_fail [n_levels].  ``out`` = (sums, n_fail)
     to ACCUMULATE into existing buffers (e.g. two views of one packed tensor that is all-reduced once)."""
     _require_cuda()
@@ -338,7 +339,7 @@ def reduce_stats(stats, status, trial0, sweep_epoch, n_levels, out=None):
     else:
         sums = torch.zeros((n_levels, 3, 3), dtype=torch.float64, device=stats.device)
         n_fail = torch.zeros((n_levels,), dtype=torch.float64, device=stats.device)
-    L.check(L.load().uvs_reduce_stats(B, int(trial0), int(sweep_epoch), int(n_levels), _ptr(stats), _ptr(status),
+    L.check(L.load().uvs_reduce_stats(B, int(trial0), int(trial_stride), int(sweep_epoch), int(n_levels), _ptr(stats), _ptr(status),
                                       _ptr(sums), _ptr(n_fail), _stream()), "uvs_reduce_stats")
     return sums, n_fail
 
