@@ -129,6 +129,22 @@ typedef struct uvs_closed_loop_cfg {
     double v_max;
     double a_max;
     double servo_gain;
+    /* Scene plant (constants decoded from scenarios/*.ttt; every field 0 = off = the ideal
+     * kinematic point-feature plant).  Launches that use any of them run the general kernel instantiations.
+     * sensor_offset: origin of the vision sensor in DH frame 6 (the scenes mount it ~(0.004, 0.007, 0.014) m off).
+     * disc_radius:   the targets are discs of this radius lying in the plane z = const (scenes: 0.0375 m); a feature is then
+     *                the CENTROID OF THE DISC'S IMAGE REGION, which is what utils.py:73-78 measures (255 sum(X mask) / sum(mask)),
+     *                evaluated on the 16-gon through the projected rim; with fov_check the region is clipped to the image
+     *                [-0.5, 255.5]^2 (a partly visible disc gives a biased centroid, as in the reference) and the trial fails
+     *                only when NOTHING of a disc is visible (0/0 -> NaN -> pinv raises, experiment.py:312-316).
+     * servo_substeps / servo_kp: the joints are position-controlled (P gain 0.1) at the 5 ms dynamics step, 10 substeps per
+     *                frame: per substep h = dt / substeps, v = kp (q_target - q) / h, limited by a_max h and v_max, q += v h,
+     *                with q_target = q + dq dt (experiment.py:320).  Without limits this equals servo_gain = 1 - (1 - kp)^substeps. */
+    double sensor_offset[3];
+    double disc_radius;
+    double servo_kp;
+    int32_t servo_substeps;
+    int32_t reserved2;
 } uvs_closed_loop_cfg;
 
 /* buffers of a closed-loop batch; any optional pointer may be NULL */

@@ -24,6 +24,8 @@ DEFAULTS = dict(
     hold_cnt=0, noise_seed=123456, pose_seed=12345, change_q_start=True,
     fov_check=False, P0=None, Q=None, R=None, targets=None, structured=False,
     v_max=0.0, a_max=0.0, servo_gain=0.0,        # joint servo model (SURVEY.md Appendix A 'Joints'); 0 = kinematic plant
+    # scene plant (include/uvs_b200.h): sensor mount offset in DH-6, finite discs, sub-stepped P servo; all 0 = off
+    sensor_offset=(0.0, 0.0, 0.0), disc_radius=0.0, servo_substeps=0, servo_kp=0.0,
 )
 
 
@@ -45,6 +47,39 @@ def servo_rate(cfg, dq, v_prev):
     if cfg.get("v_max", 0.0) > 0.0:
         v = np.minimum(np.maximum(v, -cfg["v_max"]), cfg["v_max"])
     return v
+
+
+def servo_substepped(cfg, dq, q, v_prev):
+    """csrc/kernel_args.cuh servo_substepped: P controller towards q + dq dt at h = dt / substeps under a_max / v_max."""
+    q = np.array(q, dtype=float)
+    v_prev = np.array(v_prev, dtype=float)
+    target = q + np.asarray(dq, dtype=float) * cfg["dt"]
+    h = cfg["dt"] / cfg["servo_substeps"]
+    dv = cfg.get("a_max", 0.0) * h
+    for _ in range(cfg["servo_substeps"]):
+        v = cfg["servo_kp"] * (target - q) / h
+        if cfg.get("a_max", 0.0) > 0.0:
+            v = np.minimum(np.maximum(v, v_prev - dv), v_prev + dv)
+        if cfg.get("v_max", 0.0) > 0.0:
+            v = np.minimum(np.maximum(v, -cfg["v_max"]), cfg["v_max"])
+        q = q + v * h
+        v_prev = v
+    return q, v_prev
+
+
+def scene_plant(cfg):
+    return cfg.get("disc_radius", 0.0) > 0.0 or any(v != 0.0 for v in cfg.get("sensor_offset", (0, 0, 0))) or \
+        cfg.get("servo_substeps", 0) > 0
+
+
+def measure(cfg, q, targets):
+    """Noise-free features and the 'visible' verdict under the configured plant."""
+    if scene_plant(cfg):
+        return kinematics.scene_features(q, targets, cfg.get("sensor_offset", (0, 0, 0)), cfg.get("disc_radius", 0.0),
+                                         bool(cfg["fov_check"]))
+    f = kinematics.project(q, targets)
+    z = np.repeat(kinematics.depth(q, targets), 2)
+    return f, (f >= 0.0) & (f < kinematics.RESOLUTION) & (z > 0.01) & np.isfinite(f)
 
 
 def in_view(f, z):
@@ -88,9 +123,9 @@ def run_trial(cfg, trial, noise=None, q0=None, x0=None, record=False, dq_in=None
     # experiment.py:86-117
     if x0 is not None:
         X = np.array(x0, dtype=float)
-        f = kinematics.project(q, targets) if cfg["initial_guess"] else np.zeros(m)
+        f = measure(cfg, q, targets)[0] if cfg["initial_guess"] else np.zeros(m)
     elif cfg["initial_guess"]:
-        X, f = kinematics.initial_guess(q, targets)
+        X, f = kinematics.initial_guess(q, targets, measure(cfg, q, targets)[0] if scene_plant(cfg) else None)
     else:
         X = noise_model.random_x0(cfg["noise_seed"], trial, N)
         f = np.zeros(m)
@@ -108,8 +143,8 @@ def run_trial(cfg, trial, noise=None, q0=None, x0=None, record=False, dq_in=None
     for k_it in range(T):
         t = (k_it + 1) * dt
         f_old = f.copy()
-        f_true = kinematics.project(q, targets)
-        if cfg["fov_check"] and not in_view(f_true, kinematics.depth(q, targets)):
+        f_true, visible = measure(cfg, q, targets)
+        if cfg["fov_check"] and not np.all(visible):
             status = FAIL          # NaN centroid -> pinv raises (utils.py:73-78, experiment.py:312-316)
             break
         f = f_true + noise[k_it]
@@ -150,8 +185,11 @@ def run_trial(cfg, trial, noise=None, q0=None, x0=None, record=False, dq_in=None
         k += 1
         if dq_in is not None:
             dq = np.asarray(dq_in[k_it], dtype=float)
-        v_prev = servo_rate(cfg, dq, v_prev)
-        q = q + v_prev * dt                                       # experiment.py:320,335 (v = dq without limits)
+        if cfg.get("servo_substeps", 0) > 0:
+            q, v_prev = servo_substepped(cfg, dq, q, v_prev)
+        else:
+            v_prev = servo_rate(cfg, dq, v_prev)
+            q = q + v_prev * dt                                   # experiment.py:320,335 (v = dq without limits)
     out = dict(status=status, frames=k, q_log=q_log[:k], f_log=f_log[:k], noise_log=noise_log[:k],
                t_log=t_log[:k], kernel_bw_log=bw_log[:k], dq_log=dq_log[:k],
                flags_log=flags_log[:k], epoch_log=epoch_log[:k], X=X, abort_flags=abort_flags,

@@ -111,13 +111,14 @@ def compute_Z(q, targets):
     return np.array([np.linalg.norm(t - pw) for pw in targets])
 
 
-def initial_guess(q, targets):
+def initial_guess(q, targets, f_measured=None):
     """X0 = vec_rowmajor(J_image kron(I2, R06^T) J_geom), experiment.py:94-114.
 
     The interaction rows use the RAW pixel (u, v) and the Euclidean distance,
-    exactly as the reference does.
+    exactly as the reference does.  f_measured: what the detector reports at q when the plant is not the ideal
+    point-feature pinhole (scene plant); the depth stays computeZ's DH-6-origin distance.
     """
-    f = project(q, targets)
+    f = project(q, targets) if f_measured is None else np.array(f_measured, dtype=float)
     Zc = compute_Z(q, targets)
     m = len(f)
     J_image = np.zeros((m, 6))
@@ -150,3 +151,109 @@ def camera_pose(q):
     pose[4] = np.arcsin(np.clip(-Rs[2, 0], -1.0, 1.0))
     pose[5] = np.arctan2(Rs[1, 0], Rs[0, 0])
     return pose
+
+
+# ---- scene plant (include/uvs_b200.h: sensor_offset / disc_radius) ------------------------
+DISC_VERTS = 16
+IMAGE_LO, IMAGE_HI = -0.5, 255.5
+DISC_RADIUS_SCENE = 0.0375            # scenarios/*.ttt: disc primitives of 0.075 m diameter (tag Ppr of the *_disc shapes)
+
+
+def _clip_half_plane(poly, axis, bound, sgn):
+    out = []
+    n = len(poly)
+    for i in range(n):
+        a, b = poly[i], poly[(i + 1) % n]
+        da, db = sgn * (a[axis] - bound), sgn * (b[axis] - bound)
+        ina, inb = da <= 0.0, db <= 0.0
+        if ina:
+            out.append([a[0], a[1]])
+        if ina != inb:
+            t = da / (da - db)
+            p = [a[0] + t * (b[0] - a[0]), a[1] + t * (b[1] - a[1])]
+            p[axis] = bound
+            out.append(p)
+    return out
+
+
+def disc_centroid(q, pw, offset=(0.0, 0.0, 0.0), radius=DISC_RADIUS_SCENE, clip=True):
+    """(u, v, area, depth): centroid of the image region of the disc centred at world point pw (radius `radius`, lying
+    in a plane z = const) seen by the sensor mounted at `offset` in DH frame 6 — the quantity utils.py:73-78 measures
+    (255 sum(X mask) / sum(mask)).  Same construction as csrc/ur10.cuh disc_centroid: DISC_VERTS-gon through the projected
+    rim, optional Sutherland-Hodgman clip to the image, shoelace centroid.  area = 0 (u = v = nan): nothing visible."""
+    T = fkine(q)
+    R, t = T[0:3, 0:3], T[0:3, 3]
+    off = np.asarray(offset, dtype=float)
+    c0 = R.T @ (np.asarray(pw, dtype=float) - t)
+    c1 = R.T @ (np.asarray(pw, dtype=float) + np.array([radius, 0.0, 0.0]) - t) - c0
+    c2 = R.T @ (np.asarray(pw, dtype=float) + np.array([0.0, radius, 0.0]) - t) - c0
+    c0 = c0 - off
+    poly = []
+    for i in range(DISC_VERTS):
+        ang = 2.0 * np.pi * i / DISC_VERTS
+        p = c0 + np.cos(ang) * c1 + np.sin(ang) * c2
+        if not p[2] > 0.01:
+            return np.nan, np.nan, 0.0, c0[2]
+        poly.append([PRINCIPAL + FOCAL * p[0] / p[2], PRINCIPAL + FOCAL * p[1] / p[2]])
+    outside = any(not (IMAGE_LO <= x <= IMAGE_HI and IMAGE_LO <= y <= IMAGE_HI) for x, y in poly)
+    if clip and outside:
+        poly = _clip_half_plane(poly, 0, IMAGE_LO, -1.0)
+        poly = _clip_half_plane(poly, 0, IMAGE_HI, 1.0)
+        poly = _clip_half_plane(poly, 1, IMAGE_LO, -1.0)
+        poly = _clip_half_plane(poly, 1, IMAGE_HI, 1.0)
+        if len(poly) < 3:
+            return np.nan, np.nan, 0.0, c0[2]
+    x0, y0 = poly[0]
+    a2 = cx = cy = 0.0
+    for i in range(1, len(poly) - 1):
+        ax, ay = poly[i][0] - x0, poly[i][1] - y0
+        bx, by = poly[i + 1][0] - x0, poly[i + 1][1] - y0
+        cr = ax * by - bx * ay
+        a2 += cr
+        cx += (ax + bx) * cr
+        cy += (ay + by) * cr
+    if not abs(a2) > 1e-9:
+        return np.nan, np.nan, 0.0, c0[2]
+    return x0 + cx / (3.0 * a2), y0 + cy / (3.0 * a2), 0.5 * abs(a2), c0[2]
+
+
+def scene_features(q, targets, offset=(0.0, 0.0, 0.0), radius=0.0, clip=False):
+    """f[m] and visible[m] under the scene plant: projected centres seen from the offset sensor (radius = 0) or disc
+    centroids (csrc/ur10.cuh scene_feature)."""
+    m = 2 * len(targets)
+    f = np.zeros(m)
+    vis = np.ones(m, dtype=bool)
+    off = np.asarray(offset, dtype=float)
+    T = fkine(q)
+    R, t = T[0:3, 0:3], T[0:3, 3]
+    for i, pw in enumerate(targets):
+        if radius > 0.0:
+            u, v, area, _ = disc_centroid(q, pw, off, radius, clip)
+            f[2 * i], f[2 * i + 1] = u, v
+            vis[2 * i] = vis[2 * i + 1] = area > 0.0
+        else:
+            pc = R.T @ (pw - t) - off
+            f[2 * i] = PRINCIPAL + FOCAL * pc[0] / pc[2]
+            f[2 * i + 1] = PRINCIPAL + FOCAL * pc[1] / pc[2]
+            for a in (0, 1):
+                vis[2 * i + a] = (0.0 <= f[2 * i + a] < RESOLUTION) and pc[2] > 0.01
+    return f, vis
+
+
+def rasterized_disc_centroid(q, pw, offset=(0.0, 0.0, 0.0), radius=DISC_RADIUS_SCENE):
+    """Brute force, the way the reference measures it (utils.py:73-78): every pixel (col j, row i) of the 256 x 256 image
+    whose centre ray hits the disc belongs to the mask; f = (sum(j mask) / sum(mask), sum(i mask) / sum(mask)).
+    Used by the CPU tests to pin the polygon model to the detector's semantics."""
+    T = fkine(q)
+    R, t = T[0:3, 0:3], T[0:3, 3]
+    cam = t + R @ np.asarray(offset, dtype=float)             # sensor origin in the world
+    jj, ii = np.meshgrid(np.arange(RESOLUTION), np.arange(RESOLUTION))
+    d_cam = np.stack([(jj - PRINCIPAL) / FOCAL, (ii - PRINCIPAL) / FOCAL, np.ones_like(jj, dtype=float)], axis=-1)
+    d_w = d_cam @ R.T                                          # ray directions in the world
+    s = (pw[2] - cam[2]) / d_w[..., 2]                         # intersection with the plane z = pw[2]
+    hit = cam[None, None, :] + s[..., None] * d_w
+    mask = (s > 0.01) & ((hit[..., 0] - pw[0]) ** 2 + (hit[..., 1] - pw[1]) ** 2 <= radius ** 2)
+    n = mask.sum()
+    if n == 0:
+        return np.nan, np.nan, 0
+    return float((jj * mask).sum() / n), float((ii * mask).sum() / n), int(n)

@@ -41,6 +41,7 @@ DEFAULTS = dict(
     noise_type=0, noise_params={}, hold_cnt=0,
     noise_seed=123456, pose_seed=12345, change_q_start=False, targets=None, P0=None, Q=None, R=None,
     v_max=0.0, a_max=0.0, servo_gain=0.0,
+    sensor_offset=(0.0, 0.0, 0.0), disc_radius=0.0, servo_substeps=0, servo_kp=0.0, fov_check=False,      # scene plant
 )
 
 
@@ -106,7 +107,7 @@ def run_trial(cfg, trial=0, noise=None, q0=None, x0=None, record=False):
     # initial feature vector and state (kalman_4_features.py:40,74-101; kalman_1_feature.py:44,57; kalman_3:50)
     f = np.zeros(m)
     if cfg["x0_mode"] == X0_IMAGE_JACOBIAN:
-        f = kinematics.project(q, targets)
+        f = closed_loop.measure(cfg, q, targets)[0]
     if x0 is not None:
         X = np.array(x0, dtype=float).ravel()
     elif cfg["x0_mode"] == X0_IMAGE_JACOBIAN:
@@ -129,7 +130,11 @@ def run_trial(cfg, trial=0, noise=None, q0=None, x0=None, record=False):
         if cfg["err_threshold"] >= 0.0 and not (np.linalg.norm(error) > cfg["err_threshold"]):
             break                                            # kalman_4_features.py:111
         f_old = f.copy()
-        f = kinematics.project(q, targets) + noise[k_it]
+        f_true, visible = closed_loop.measure(cfg, q, targets)
+        if cfg.get("fov_check") and not np.all(visible):
+            status = FAIL
+            break
+        f = f_true + noise[k_it]
         kappa = np.ones(m)
         if method == filters.ANALYTICAL:
             J = image_jacobian(f, depths(q, targets, cfg["depth_mode"]), cfg["focal"])
@@ -162,8 +167,11 @@ def run_trial(cfg, trial=0, noise=None, q0=None, x0=None, record=False):
         if record:
             X_log[k] = X
         k += 1
-        v_prev = closed_loop.servo_rate(cfg, dq, v_prev)
-        q = q + v_prev * dt
+        if cfg.get("servo_substeps", 0) > 0:
+            q, v_prev = closed_loop.servo_substepped(cfg, dq, q, v_prev)
+        else:
+            v_prev = closed_loop.servo_rate(cfg, dq, v_prev)
+            q = q + v_prev * dt
     out = dict(status=status, frames=k, q_log=q_log[:k], f_log=f_log[:k], noise_log=noise_log[:k],
                t_log=t_log[:k], dp_log=dp_log[:k], dq_log=dq_log[:k], X=X, P=P, q_final=q)
     out["stats"] = stats_mod.trial_stats(out["t_log"], out["f_log"], desired)

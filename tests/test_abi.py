@@ -33,18 +33,20 @@ def test_every_declared_symbol_is_exported(lib):
 def test_struct_layout_matches_c(lib, tmp_path):
     src = tmp_path / "sz.c"
     src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "uvs_b200.h"\n'
-                   'int main(){printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu\\n", sizeof(uvs_filter_params), sizeof(uvs_noise_params),'
+                   'int main(){printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu\\n", sizeof(uvs_filter_params), sizeof(uvs_noise_params),'
                    'sizeof(uvs_closed_loop_cfg), sizeof(uvs_closed_loop_io), offsetof(uvs_closed_loop_cfg, sweep),'
                    'offsetof(uvs_closed_loop_cfg, P0), offsetof(uvs_closed_loop_io, p_layout), sizeof(uvs_twist_cfg),'
                    'offsetof(uvs_twist_cfg, err_threshold), offsetof(uvs_closed_loop_cfg, servo_gain),'
-                   'offsetof(uvs_closed_loop_io, flags_log), offsetof(uvs_twist_cfg, stale_fk));return 0;}\n')
+                   'offsetof(uvs_closed_loop_io, flags_log), offsetof(uvs_twist_cfg, stale_fk),'
+                   'offsetof(uvs_closed_loop_cfg, servo_substeps));return 0;}\n')
     exe = tmp_path / "sz"
     subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)])
     got = [int(v) for v in subprocess.check_output([str(exe)]).split()]
     want = [C.sizeof(lib.FilterParams), C.sizeof(lib.NoiseParams), C.sizeof(lib.ClosedLoopCfg),
             C.sizeof(lib.ClosedLoopIO), lib.ClosedLoopCfg.sweep.offset, lib.ClosedLoopCfg.P0.offset,
             lib.ClosedLoopIO.p_layout.offset, C.sizeof(lib.TwistCfg), lib.TwistCfg.err_threshold.offset,
-            lib.ClosedLoopCfg.servo_gain.offset, lib.ClosedLoopIO.flags_log.offset, lib.TwistCfg.stale_fk.offset]
+            lib.ClosedLoopCfg.servo_gain.offset, lib.ClosedLoopIO.flags_log.offset, lib.TwistCfg.stale_fk.offset,
+            lib.ClosedLoopCfg.servo_substeps.offset]
     assert got == want
 
 

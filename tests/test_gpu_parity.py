@@ -676,6 +676,72 @@ def test_servo_limits_match_oracle(uvs, limits):
         E.closed_loop(bad, 0, 1)
 
 
+SCENE = dict(sensor_offset=(0.004, 0.007, 0.014), disc_radius=0.0375, servo_substeps=10, servo_kp=0.1, v_max=1.0472,
+             a_max=6.283)
+
+
+@pytest.mark.parametrize("fov", [False, True], ids=["unbounded", "clipped"])
+def test_scene_plant_matches_oracle(uvs, fov):
+    """SURVEY 8f row 3, the rest of it: sensor mount offset, finite-disc centroid (clipped to the image with fov_check) and
+    the sub-stepped position servo (P gain 0.1 at the 5 ms dynamics step, 60 deg/s, 360 deg/s^2), both kernel families
+    against the oracle's closed loop on the same Philox streams.  Start poses include ones where a disc is partly outside
+    the image (q[1] near 0): with fov_check those run on a clipped centroid instead of failing at once."""
+    from oracle import closed_loop as CL, noise_model as NM
+    L, E = uvs._lib, uvs.engine
+    B, trial0 = 8, 20
+    npar = dict(alpha=1.6, beta=0.0, gamma=1.0, delta=0.0)
+    ocfg = CL.make_cfg(method=METHODS["GMCKF"], annealing=True, noise_type=NM.ALPHA_STABLE, noise_params=npar,
+                       noise_seed=5, pose_seed=8, fov_check=fov, **SCENE)
+    ref = [CL.run_trial(ocfg, trial0 + b) for b in range(B)]
+    plain = CL.run_trial(CL.make_cfg(method=METHODS["GMCKF"], annealing=True, noise_type=NM.ALPHA_STABLE, noise_params=npar,
+                                     noise_seed=5, pose_seed=8), trial0)
+    if ref[0]["frames"] == plain["frames"]:
+        assert np.abs(ref[0]["q_log"] - plain["q_log"]).max() > 1e-3           # the scene plant is a different plant
+    if fov:
+        assert any(r["status"] == 0 for r in ref)
+    for mode in (L.MODE_DENSE, L.MODE_BLOCKDIAG):
+        p = E.filter_params(METHODS["GMCKF"], 4, mode=mode, annealing=True)
+        cfg = E.closed_loop_cfg(p, E.noise_params(NM.ALPHA_STABLE, seed=5, **npar), T=300, dt=0.05, ibvs_gain=0.2,
+                                q_start=ocfg["q_start"], desired_f=ocfg["desired_f"], pose_seed=8, fov_check=fov, **SCENE)
+        out = E.closed_loop(cfg, trial0, B, want_log=True)
+        log, st = out["log"].cpu().numpy(), out["stats"].cpu().numpy()
+        status, frames = out["status"].cpu().numpy(), out["frames"].cpu().numpy()
+        for b in range(B):
+            n = min(tame_prefix(ref[b]["dq_log"]), ref[b]["frames"])
+            if ref[b]["frames"] == 0:
+                assert status[b] == 1 and frames[b] == 0                         # a disc fully out of view at the start
+                continue
+            assert n >= 5
+            assert rel_err(log[b, :n, 0:6], ref[b]["q_log"][:n]) <= 1e-6, (mode, b)
+            assert rel_err(log[b, :n, 6:14], ref[b]["f_log"][:n]) <= 1e-6, (mode, b)
+            if n == ref[b]["frames"]:
+                assert status[b] == ref[b]["status"] and frames[b] == ref[b]["frames"]
+                assert rel_err(st[b], ref[b]["stats"]) <= 1e-6, (mode, b)
+
+
+def test_scene_plant_pieces(uvs):
+    """(a) the sub-stepped servo without limits is the first-order lag servo_gain = 1 - (1 - kp)^substeps; (b) the sensor
+    offset alone shifts the features exactly as the oracle's projection says; (c) bad arguments are rejected."""
+    from oracle import closed_loop as CL, kinematics as K, noise_model as NM
+    L, E = uvs._lib, uvs.engine
+    q0 = CL.DEFAULTS["q_start"]
+    common = dict(T=40, dt=0.05, ibvs_gain=0.2, q_start=[0.0, -0.3, 1.96349541, 0.0, -1.57079633, 0.0],
+                  desired_f=CL.DEFAULTS["desired_f"], change_q_start=False)
+    for mode in (L.MODE_DENSE, L.MODE_BLOCKDIAG):
+        p = E.filter_params(METHODS["KF"], 4, mode=mode)
+        nz = E.noise_params(NM.WHITE_NOISE, seed=3, std=1.0)
+        a = E.closed_loop(E.closed_loop_cfg(p, nz, servo_substeps=10, servo_kp=0.1, **common), 0, 2, want_log=True)
+        b = E.closed_loop(E.closed_loop_cfg(p, nz, servo_gain=1.0 - 0.9 ** 10, **common), 0, 2, want_log=True)
+        assert rel_err(a["log"].cpu().numpy(), b["log"].cpu().numpy()) <= 1e-9
+        off = (0.004, 0.007, 0.014)
+        c = E.closed_loop(E.closed_loop_cfg(p, E.noise_params(L.NOISE_NONE), sensor_offset=off, **common), 0, 1, want_log=True)
+        f0 = c["log"].cpu().numpy()[0, 0, 6:14]
+        assert rel_err(f0, K.scene_features(np.array(common["q_start"]), K.TARGETS[4], off)[0]) <= 1e-12
+        for bad in (dict(disc_radius=-1.0), dict(servo_substeps=10, servo_kp=0.0), dict(servo_substeps=-2, servo_kp=0.1)):
+            with pytest.raises(L.UvsError):
+                E.closed_loop(E.closed_loop_cfg(p, nz, **common, **bad), 0, 1)
+
+
 def test_long_trials_without_bandwidth_table(uvs):
     """T > 1024 frames: the closed-loop kernel computes the annealed bandwidth per frame instead of reading its per-CTA
     table (csrc/dense_kernels.cuh: kSigmaTableMax); same trajectory as the oracle."""

@@ -223,3 +223,26 @@ def test_twist_loop_rank_deficient_jacobian(uvs, nf):
         step = log[b, 1, :6] - log[b, 0, :6]
         step_ref = ref["q_log"][1] - ref["q_log"][0]
         assert rel_err(step, step_ref) <= 1e-8, (nf, b, step, step_ref)
+
+
+def test_twist_loop_scene_plant(uvs):
+    """The scene plant (sensor offset, finite discs, sub-stepped servo) in the camera-twist pipeline, against the oracle."""
+    from oracle import twist_loop
+    L, E = uvs._lib, uvs.engine
+    scene = dict(sensor_offset=(0.004, 0.007, 0.014), disc_radius=0.0375, servo_substeps=10, servo_kp=0.1, v_max=1.0472, a_max=6.283)
+    ocfg = twist_loop.make_cfg(method=2, nf=4, T=120, gain=0.5, noise_type=1, noise_params=dict(std=1.0), **scene)
+    cfg, tw = gpu_cfg(uvs, ocfg, noise=_noise_params(uvs, ocfg))
+    for k, v in scene.items():
+        if k == "sensor_offset":
+            for i in range(3):
+                cfg.sensor_offset[i] = v[i]
+        else:
+            setattr(cfg, k, v)
+    out = E.twist_loop(cfg, tw, 2, 2, want_log=True)
+    log = out["log"].cpu().numpy()
+    for b in range(2):
+        ref = twist_loop.run_trial(ocfg, 2 + b)
+        k = ref["frames"]
+        assert int(out["frames"][b]) == k
+        assert rel_err(log[b, :k, :6], ref["q_log"]) <= 1e-8
+        assert rel_err(log[b, :k, 6:14], ref["f_log"]) <= 1e-8

@@ -203,3 +203,36 @@ def test_twist_loop_threshold_stops_the_trial():
     err = np.linalg.norm(res["f_log"] - np.asarray(cfg["desired_f"]), axis=1)
     assert 1 < res["frames"] < int(g["T"])
     assert err[-1] <= 2.5 and np.all(err[:-1] > 2.5)
+
+
+def test_disc_centroid_model_matches_the_detector():
+    """the finite-disc feature model (16-gon through the projected rim, clipped to the image, shoelace
+    centroid — oracle/kinematics.py, csrc/ur10.cuh) against a brute-force rasterisation that measures what
+    /root/reference/utils.py:73-78 measures (centroid of the mask pixels): within the pixel-quantisation noise for fully
+    visible, partly clipped and invisible discs.  Disc radius 0.0375 m is the scenes' (scenarios/*.ttt, tag Ppr)."""
+    from oracle import kinematics as K
+    rng = np.random.default_rng(3)
+    base = np.array([0.0, -0.25, 1.96349541, 0.0, -1.57079633, 0.0])
+    n_clipped = n_full = 0
+    for trial in range(40):
+        q = base + np.array([rng.uniform(-0.35, 0.0), rng.uniform(-0.45, 0.25), 0, 0, 0, 0])
+        off = (0.004, 0.007, 0.014) if trial % 2 else (0.0, 0.0, 0.0)
+        for pw in K.TARGETS[4]:
+            u, v, area, depth = K.disc_centroid(q, pw, off, K.DISC_RADIUS_SCENE, clip=True)
+            ru, rv, n = K.rasterized_disc_centroid(q, pw, off, K.DISC_RADIUS_SCENE)
+            if n == 0:
+                assert area < 3.0                                  # nothing (or a sliver below one pixel) visible
+                continue
+            if area == 0.0:
+                assert n <= 3
+                continue
+            if n < 60:
+                continue                                           # slivers: the raster centroid itself is +-0.5 px
+            assert abs(u - ru) < 0.3 and abs(v - rv) < 0.3, (trial, pw, u, v, ru, rv)
+            assert abs(area / n - 0.974) < 0.08                    # inscribed 16-gon: sin(pi/8) / (pi/8) = 0.974 of the disc
+            full = K.disc_centroid(q, pw, off, K.DISC_RADIUS_SCENE, clip=False)
+            if abs(full[2] - area) > 1e-9:
+                n_clipped += 1
+            else:
+                n_full += 1
+    assert n_clipped >= 5 and n_full >= 40

@@ -53,14 +53,15 @@ def main():
             E.twist_loop(cfg, E.twist_cfg(x0_mode=L.X0_IMAGE_JACOBIAN, focal_x0=512.0, focal=512.0), 0, B, want_log=True,
                          want_state=True)
     # zero initial Jacobian: the pseudo-inverse meets a rank-deficient Gram matrix on the first frames, so the cooperative
-    # Jacobi fallback (pinv_fallback_coop: dense M = 6, block-diagonal M >= 6, twist) and the serial one (dense M = 8) run
-    for nf in (4, 3):
+    # one-sided Jacobi fallback (pinv_fallback_osj) runs in every family and for every M, with the per-frame trace on
+    for nf in (4, 3, 1):
         m, N = 2 * nf, 12 * nf
         X0 = torch.zeros(B, N, dtype=torch.float64, device="cuda")
         for mode in (L.MODE_DENSE, L.MODE_BLOCKDIAG):
             p = E.filter_params(L.METHOD_KF, nf, mode=mode)
             cfg = E.closed_loop_cfg(p, noise, T=T, dt=0.05, ibvs_gain=0.2, q_start=Q_START, desired_f=DESIRED[nf])
-            out = E.closed_loop(cfg, 0, B, X0_in=X0)
+            out = E.closed_loop(cfg, 0, B, X0_in=X0, want_trace=True,
+                                dq_in=0.01 * torch.randn(B, T, 6, dtype=torch.float64, device="cuda"))
             assert int((out["flags"] & L.FLAG_RANK_DEFICIENT).ne(0).sum()) == B
         p = E.filter_params(L.METHOD_KF, nf, mode=L.MODE_DENSE)
         cfg = E.closed_loop_cfg(p, noise, T=T, dt=0.05, ibvs_gain=0.3, q_start=Q_START, desired_f=DESIRED[nf])
@@ -73,6 +74,10 @@ def main():
     E.ibvs(4, J, torch.randn(B, 8, dtype=torch.float64, device="cuda"), None, 0.2)
     st = torch.rand(B, 3, dtype=torch.float64, device="cuda")
     E.reduce_stats(st, torch.zeros(B, dtype=torch.int32, device="cuda"), 0, 4, 6)
+    # log streaming: two streams, two device + two page-locked host buffers
+    p = E.filter_params(L.METHOD_GMCKF, 4, mode=L.MODE_BLOCKDIAG, annealing=True)
+    cfg = E.closed_loop_cfg(p, noise, T=T, dt=0.05, ibvs_gain=0.2, q_start=Q_START, desired_f=DESIRED[4])
+    E.closed_loop_stream(cfg, 0, 50, chunk=16, sink=lambda *a: 0)
     torch.cuda.synchronize()
     print("sanitize.py: all launches done")
 

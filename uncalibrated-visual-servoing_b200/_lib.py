@@ -45,7 +45,9 @@ class ClosedLoopCfg(C.Structure):
                 ("sweep_epoch", C.c_int32), ("sweep_param", C.c_int32), ("trial_stride", C.c_int32),
                 ("dt", C.c_double), ("ibvs_gain", C.c_double), ("q_start", C.c_double * 6),
                 ("desired_f", C.c_double * 8), ("targets", C.c_double * 12), ("pose_seed", C.c_uint64),
-                ("sweep", C.c_double * UVS_MAX_SWEEP), ("P0", _dp), ("v_max", C.c_double), ("a_max", C.c_double), ("servo_gain", C.c_double)]
+                ("sweep", C.c_double * UVS_MAX_SWEEP), ("P0", _dp), ("v_max", C.c_double), ("a_max", C.c_double), ("servo_gain", C.c_double),
+                ("sensor_offset", C.c_double * 3), ("disc_radius", C.c_double), ("servo_kp", C.c_double),
+                ("servo_substeps", C.c_int32), ("reserved2", C.c_int32)]
 
 
 class ClosedLoopIO(C.Structure):

@@ -119,6 +119,9 @@ static int check_loop_cfg(const uvs_closed_loop_cfg& c) {
     if (c.sweep_param < 0 || c.sweep_param > 2) return set_error(UVS_ERR_INVALID, "sweep_param must be 0, 1 or 2 (got %d)", c.sweep_param);
     if (c.sweep_len > 0 && c.sweep_epoch < 1) return set_error(UVS_ERR_INVALID, "sweep_epoch must be >= 1 (got %d)", c.sweep_epoch);
     if (c.trial_stride < 0) return set_error(UVS_ERR_INVALID, "trial_stride must be >= 0 (got %d)", c.trial_stride);
+    if (!(c.disc_radius >= 0.0)) return set_error(UVS_ERR_INVALID, "disc_radius must be >= 0 (got %g)", c.disc_radius);
+    if (c.servo_substeps < 0 || c.servo_substeps > 1000) return set_error(UVS_ERR_INVALID, "servo_substeps must be in [0, 1000] (got %d)", c.servo_substeps);
+    if (c.servo_substeps > 0 && !(c.servo_kp > 0.0 && c.servo_kp <= 1.0)) return set_error(UVS_ERR_INVALID, "servo_kp must be in (0, 1] (got %g)", c.servo_kp);
     if (!(c.v_max >= 0.0) || !(c.a_max >= 0.0) || !(c.servo_gain >= 0.0))
         return set_error(UVS_ERR_INVALID, "v_max / a_max / servo_gain must be >= 0");
     return 0;

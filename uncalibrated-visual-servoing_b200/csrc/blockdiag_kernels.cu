@@ -320,9 +320,17 @@ __global__ void __launch_bounds__(128, UVS_BD_MINB) bd_closed_loop_kernel(const 
             ur10_fk(q, T6, &kin);
             const double* pw = cfg.targets + 3 * (row >> 1);
             double depth;
-            const double u = project_coord(T6, pw, 0, depth);
-            const double v = project_coord(T6, pw, 1, depth);
-            const double zc = camera_distance(T6, pw);
+            double u = project_coord(T6, pw, 0, depth);
+            double v = project_coord(T6, pw, 1, depth);
+            const double zc = camera_distance(T6, pw);               // computeZ: DH-6 origin to disc centre, whatever the plant
+            if (EXTRAS && scene_plant(cfg)) {                            // what the detector measures at the start pose
+                double sn0[6], cs0[6];
+                bool vis;
+#pragma unroll
+                for (int j = 0; j < 6; ++j) sincos(dh_theta(j, q[j]), &sn0[j], &cs0[j]);
+                u = scene_feature(sn0, cs0, pw, cfg, 0, depth, vis);
+                v = scene_feature(sn0, cs0, pw, cfg, 1, depth, vis);
+            }
             if (a.io.X0_in) {
 #pragma unroll
                 for (int i = 0; i < 6; ++i) s.x[i] = a.io.X0_in[bb * N + 6 * row + i];
@@ -360,11 +368,18 @@ __global__ void __launch_bounds__(128, UVS_BD_MINB) bd_closed_loop_kernel(const 
             // back through the chain into the camera frame (ur10_simulation.py:97-110 + Appendix A pixel model)
             double sn[6], cs[6], pc[3];
             ur10_sincos_group<GS>(q, gl, sn, cs);
-            ur10_point_in_camera(sn, cs, cfg.targets + 3 * (row >> 1), pc);
-            const double f_true = pixel_of(pc, row & 1);
-            const double depth = pc[2];
+            double f_true, depth;
+            bool visible;
+            if (EXTRAS && scene_plant(cfg)) {
+                f_true = scene_feature(sn, cs, cfg.targets + 3 * (row >> 1), cfg, row & 1, depth, visible);
+            } else {
+                ur10_point_in_camera(sn, cs, cfg.targets + 3 * (row >> 1), pc);
+                f_true = pixel_of(pc, row & 1);
+                depth = pc[2];
+                visible = (f_true >= 0.0 && f_true < kResolution && depth > kMinDepth);
+            }
             if (cfg.fov_check) {
-                const bool bad = own && !(f_true >= 0.0 && f_true < kResolution && depth > kMinDepth);
+                const bool bad = own && !visible;
                 if (group_any<GS>(bad) && alive) { alive = false; status = UVS_STATUS_FAIL; flags_all |= UVS_FLAG_OUT_OF_VIEW; }
             }
             double nz;
@@ -441,9 +456,13 @@ __global__ void __launch_bounds__(128, UVS_BD_MINB) bd_closed_loop_kernel(const 
 #pragma unroll
                 for (int r = 0; r < 6; ++r) {
                     dq[r] = dq_new[r];
-                    double v = dq[r];
-                    if (servo) { v = servo_rate(cfg, dq[r], v_prev[r]); v_prev[r] = v; }
-                    q[r] += v * cfg.dt;
+                    if (EXTRAS && cfg.servo_substeps > 0) {
+                        servo_substepped(cfg, dq[r], q[r], v_prev[r]);
+                    } else {
+                        double v = dq[r];
+                        if (servo) { v = servo_rate(cfg, dq[r], v_prev[r]); v_prev[r] = v; }
+                        q[r] += v * cfg.dt;
+                    }
                 }
             }
         }
@@ -505,7 +524,7 @@ static cudaError_t bd_closed_launch(const ClosedLoopArgs& a, int sms, cudaStream
     const long long need = (warps + 3) / 4;
     const uvs_closed_loop_io& io = a.io;
     const bool extras = (a.cfg.v_max > 0.0) || (a.cfg.a_max > 0.0) || (a.cfg.servo_gain > 0.0 && a.cfg.servo_gain != 1.0) ||
-                        io.dq_in || io.X_log || io.P_log || io.dq_log || io.kappa_log || io.flags_log;
+                        io.dq_in || io.X_log || io.P_log || io.dq_log || io.kappa_log || io.flags_log || scene_plant(a.cfg);
     if (extras)
         bd_closed_loop_kernel<M, METHOD, true><<<(int)bd_grid(bd_closed_loop_kernel<M, METHOD, true>, need, sms), 128, 0, st>>>(a);
     else

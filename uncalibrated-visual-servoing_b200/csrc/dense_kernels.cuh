@@ -154,7 +154,17 @@ __global__ void UVS_DENSE_BOUNDS dense_closed_loop_kernel(const __grid_constant_
                 const double* pw = cfg.targets + 3 * (lane >> 1);
                 u = project_coord(T6, pw, 0, depth);
                 v = project_coord(T6, pw, 1, depth);
-                zc = camera_distance(T6, pw);
+                zc = camera_distance(T6, pw);                       // computeZ: DH-6 origin to disc centre, whatever the plant
+                if constexpr (!FAST) {
+                    if (scene_plant(cfg)) {                             // what the detector measures at the start pose
+                        double sn0[6], cs0[6];
+                        bool vis;
+#pragma unroll
+                        for (int j = 0; j < 6; ++j) sincos(dh_theta(j, q[j]), &sn0[j], &cs0[j]);
+                        u = scene_feature(sn0, cs0, pw, cfg, 0, depth, vis);
+                        v = scene_feature(sn0, cs0, pw, cfg, 1, depth, vis);
+                    }
+                }
             }
             if (a.io.X0_in) {
                 for (int r = lane; r < N; r += 32) w.X[r] = a.io.X0_in[b * N + r];
@@ -211,6 +221,7 @@ __global__ void UVS_DENSE_BOUNDS dense_closed_loop_kernel(const __grid_constant_
             }
             __syncwarp();
             double f_true = 0.0, depth = 1.0;
+            bool visible = true;
             if (lane < M) {
                 double sn[6], cs[6], pc[3];
 #pragma unroll
@@ -218,12 +229,19 @@ __global__ void UVS_DENSE_BOUNDS dense_closed_loop_kernel(const __grid_constant_
                     const double2 t = *reinterpret_cast<const double2*>(w.sc + 2 * j);
                     sn[j] = t.x; cs[j] = t.y;
                 }
-                ur10_point_in_camera(sn, cs, target, pc);
-                f_true = kPrincipal + fast_div(kFocal * ((lane & 1) ? pc[1] : pc[0]), pc[2]);    // pixel_of()
-                depth = pc[2];
+                bool scene = false;
+                if constexpr (!FAST) scene = scene_plant(cfg);
+                if (scene) {
+                    f_true = scene_feature(sn, cs, target, cfg, lane & 1, depth, visible);
+                } else {
+                    ur10_point_in_camera(sn, cs, target, pc);
+                    f_true = kPrincipal + fast_div(kFocal * ((lane & 1) ? pc[1] : pc[0]), pc[2]);    // pixel_of()
+                    depth = pc[2];
+                    visible = (f_true >= 0.0 && f_true < kResolution && depth > kMinDepth);
+                }
             }
             if (cfg.fov_check) {
-                const bool bad = (lane < M) && !(f_true >= 0.0 && f_true < kResolution && depth > kMinDepth);
+                const bool bad = (lane < M) && !visible;
                 if (__any_sync(UVS_FULL_MASK, bad)) {                   // NaN centroid -> FAIL
                     status = UVS_STATUS_FAIL; flags_all |= UVS_FLAG_OUT_OF_VIEW; break;
                 }
@@ -299,9 +317,17 @@ __global__ void UVS_DENSE_BOUNDS dense_closed_loop_kernel(const __grid_constant_
             if (a.io.dq_in && lane < 6) dq_l = a.io.dq_in[((size_t)b * T + k) * 6 + lane];     // replay gate: recorded command
             if (lane < 6) {                                              // experiment.py:320,335
                 w.dq[lane] = dq_l;
-                double v = dq_l;
-                if (servo) { v = servo_rate(cfg, dq_l, v_prev); v_prev = v; }
-                w.q[lane] = q_l + v * cfg.dt;
+                bool substepped = false;
+                if constexpr (!FAST) substepped = cfg.servo_substeps > 0;
+                if (substepped) {
+                    double qn = q_l;
+                    servo_substepped(cfg, dq_l, qn, v_prev);
+                    w.q[lane] = qn;
+                } else {
+                    double v = dq_l;
+                    if (servo) { v = servo_rate(cfg, dq_l, v_prev); v_prev = v; }
+                    w.q[lane] = q_l + v * cfg.dt;
+                }
             }
             __syncwarp();
         }
@@ -360,7 +386,7 @@ static cudaError_t dense_launch(Kernel kernel, const Args& a, long long B, size_
     }                                                                                                        \
     template <int METHOD> static cudaError_t closed_one_##MM(const ClosedLoopArgs& a, int sms, cudaStream_t st) { \
         const uvs_filter_params& fp = a.cfg.filt;                                                            \
-        if (UVS_DENSE_FAST && fp.Q == nullptr && fp.R == nullptr && fp.joseph)                               \
+        if (UVS_DENSE_FAST && fp.Q == nullptr && fp.R == nullptr && fp.joseph && !scene_plant(a.cfg))        \
             return dense_launch(dense_closed_loop_kernel<MM, METHOD, UVS_DENSE_FAST != 0>, a, a.B,           \
                                 dense_smem_bytes<MM, METHOD == UVS_METHOD_MCKF>(kDenseWarps) +               \
                                     sigma_table_bytes(a.cfg.T), sms, st);                                    \

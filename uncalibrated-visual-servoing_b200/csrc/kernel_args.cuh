@@ -83,6 +83,22 @@ UVS_DEV double servo_rate(const uvs_closed_loop_cfg& cfg, double dq, double v_pr
     return v;
 }
 
+// One frame of the sub-stepped position servo (uvs_closed_loop_cfg.servo_substeps / servo_kp): the joint runs a P
+// controller towards q_target = q + dq dt (experiment.py:320) at the dynamics step h = dt / substeps, under the scenes'
+// acceleration / velocity limits.  q and v_prev (the joint rate of the last substep) are updated in place.
+UVS_DEV void servo_substepped(const uvs_closed_loop_cfg& cfg, double dq, double& q, double& v_prev) {
+    const double target = q + dq * cfg.dt;
+    const double h = cfg.dt / (double)cfg.servo_substeps;
+    const double dv = cfg.a_max * h;
+    for (int s = 0; s < cfg.servo_substeps; ++s) {
+        double v = cfg.servo_kp * (target - q) / h;
+        if (cfg.a_max > 0.0) v = fmin(fmax(v, v_prev - dv), v_prev + dv);
+        if (cfg.v_max > 0.0) v = fmin(fmax(v, -cfg.v_max), cfg.v_max);
+        q += v * h;
+        v_prev = v;
+    }
+}
+
 UVS_DEV void start_pose(const uvs_closed_loop_cfg& cfg, uint64_t trial, double (&q)[6]) {
 #pragma unroll
     for (int j = 0; j < 6; ++j) q[j] = cfg.q_start[j];

@@ -124,6 +124,14 @@ __global__ void __launch_bounds__(kTwistThreads, 2) twist_closed_loop_kernel(con
                 u = project_coord(T6, target, 0, depth);
                 v = project_coord(T6, target, 1, depth);
                 zc = (tw.depth_mode == UVS_DEPTH_HEIGHT) ? T6.p[2] : camera_distance(T6, target);
+                if (scene_plant(cfg)) {
+                    double sn0[6], cs0[6];
+                    bool vis;
+#pragma unroll
+                    for (int j = 0; j < 6; ++j) sincos(dh_theta(j, q[j]), &sn0[j], &cs0[j]);
+                    u = scene_feature(sn0, cs0, target, cfg, 0, depth, vis);
+                    v = scene_feature(sn0, cs0, target, cfg, 1, depth, vis);
+                }
             }
             if (tw.x0_mode == UVS_X0_IMAGE_JACOBIAN && lane < M) f_l = (lane & 1) ? v : u;
             if (a.io.X0_in) {
@@ -176,6 +184,9 @@ __global__ void __launch_bounds__(kTwistThreads, 2) twist_closed_loop_kernel(con
             __syncwarp();
             Tf T6;
             double zax[3], org[3];
+            double f_scene = 0.0, depth_scene = 1.0;
+            bool vis_scene = true;
+            const bool scene = scene_plant(cfg);
             {
                 double sn[6], cs[6];
 #pragma unroll
@@ -184,6 +195,7 @@ __global__ void __launch_bounds__(kTwistThreads, 2) twist_closed_loop_kernel(con
                     sn[j] = t.x; cs[j] = t.y;
                 }
                 ur10_chain_columns(sn, cs, lane, T6, zax, org);
+                if (scene && lane < M) f_scene = scene_feature(sn, cs, target, cfg, lane & 1, depth_scene, vis_scene);
             }
             // tw.stale_fk: the scripts that never refresh UR10Simulation's cached transforms inside the loop keep the
             // start pose's J_geom and R06 (kalman_4_features.py:165-169; frame 0 is at the start pose)
@@ -199,12 +211,15 @@ __global__ void __launch_bounds__(kTwistThreads, 2) twist_closed_loop_kernel(con
                 ts.Jg[5 * 6 + lane] = zax[2];
             }
             double f_true = 0.0, depth = 1.0, zc = 1.0;
+            bool visible = true;
             if (lane < M) {
                 f_true = project_coord(T6, target, lane & 1, depth);
+                visible = (f_true >= 0.0 && f_true < kResolution && depth > kMinDepth);
+                if (scene) { f_true = f_scene; depth = depth_scene; visible = vis_scene; }
                 zc = (tw.depth_mode == UVS_DEPTH_HEIGHT) ? T6.p[2] : camera_distance(T6, target);
             }
             if (cfg.fov_check) {
-                const bool bad = (lane < M) && !(f_true >= 0.0 && f_true < kResolution && depth > kMinDepth);
+                const bool bad = (lane < M) && !visible;
                 if (__any_sync(UVS_FULL_MASK, bad)) {
                     status = UVS_STATUS_FAIL; flags_all |= UVS_FLAG_OUT_OF_VIEW; break;
                 }
@@ -303,9 +318,13 @@ __global__ void __launch_bounds__(kTwistThreads, 2) twist_closed_loop_kernel(con
 #pragma unroll
             for (int r = 0; r < 6; ++r) {
                 if (lane == r) w.dq[r] = dp[r];
-                double v = dq[r];
-                if (servo) { v = servo_rate(cfg, dq[r], v_prev[r]); v_prev[r] = v; }
-                q[r] += v * cfg.dt;                                        // kalman_4_features.py:173,192
+                if (cfg.servo_substeps > 0) {
+                    servo_substepped(cfg, dq[r], q[r], v_prev[r]);
+                } else {
+                    double v = dq[r];
+                    if (servo) { v = servo_rate(cfg, dq[r], v_prev[r]); v_prev[r] = v; }
+                    q[r] += v * cfg.dt;                                    // kalman_4_features.py:173,192
+                }
             }
             __syncwarp();
         }

@@ -82,6 +82,111 @@ UVS_DEV void ur10_point_in_camera(const double (&s)[6], const double (&c)[6], co
     dh_inv_point<1, 0>(pc, s[5], c[5], 0.0922, 0.0);
 }
 
+// ---- scene plant (uvs_closed_loop_cfg.sensor_offset / disc_radius) ------------------------
+// The reference measures a feature as the centroid of the pixels of a coloured disc (utils.py:73-78:
+// 255 sum(X mask) / sum(mask) on the flipped 256 x 256 image).  Here the disc (radius r, lying in a plane z = const of
+// the world, as in the scenes) is seen through the pinhole as the polygon through kDiscVerts projected rim points; its
+// centroid (shoelace formula) is the feature.  With `clip` the polygon is first clipped to the image area
+// [-0.5, 255.5]^2 (Sutherland-Hodgman): a partly visible disc yields a biased centroid, a disc with no visible part
+// yields area 0 (the reference: 0/0 = NaN -> np.linalg.pinv raises -> FAIL).
+constexpr int kDiscVerts = 16;
+constexpr double kImageLo = -0.5, kImageHi = 255.5;
+
+// one Sutherland-Hodgman pass against the half plane  sgn * (coord[axis] - bound) <= 0;  returns the new count
+UVS_DEV int clip_half_plane(const double (*in)[2], int n, double (*out)[2], int axis, double bound, double sgn) {
+    int m = 0;
+    for (int i = 0; i < n; ++i) {
+        const double* a = in[i];
+        const double* b = in[(i + 1 == n) ? 0 : i + 1];
+        const double da = sgn * (a[axis] - bound), db = sgn * (b[axis] - bound);
+        const bool ina = da <= 0.0, inb = db <= 0.0;
+        if (ina) { out[m][0] = a[0]; out[m][1] = a[1]; ++m; }
+        if (ina != inb) {
+            const double t = da / (da - db);
+            out[m][0] = a[0] + t * (b[0] - a[0]);
+            out[m][1] = a[1] + t * (b[1] - a[1]);
+            out[m][axis] = bound;
+            ++m;
+        }
+    }
+    return m;
+}
+
+// Centroid (u, v) of the image region of the disc centred at pw, given sin / cos of the DH angles.  off = sensor origin
+// in DH frame 6.  Returns the signed-area magnitude of the (clipped) region in px^2: 0 = nothing visible.
+// depth = z of the disc centre in the sensor frame.
+UVS_DEV double disc_centroid(const double (&sn)[6], const double (&cs)[6], const double* pw, const double* off, double radius,
+                             bool clip, double& u, double& v, double& depth) {
+    double c0[3], c1[3], c2[3];
+    const double px[3] = {pw[0] + radius, pw[1], pw[2]}, py[3] = {pw[0], pw[1] + radius, pw[2]};
+    ur10_point_in_camera(sn, cs, pw, c0);
+    ur10_point_in_camera(sn, cs, px, c1);
+    ur10_point_in_camera(sn, cs, py, c2);
+#pragma unroll
+    for (int j = 0; j < 3; ++j) { c1[j] -= c0[j]; c2[j] -= c0[j]; c0[j] -= off[j]; }      // rim axes; centre in the sensor frame
+    depth = c0[2];
+    double poly[kDiscVerts + 4][2], tmp[kDiscVerts + 4][2];
+    bool behind = false, outside = false;
+    for (int i = 0; i < kDiscVerts; ++i) {
+        double sa, ca;
+        sincospi(2.0 * i / kDiscVerts, &sa, &ca);
+        const double x = c0[0] + ca * c1[0] + sa * c2[0], y = c0[1] + ca * c1[1] + sa * c2[1], z = c0[2] + ca * c1[2] + sa * c2[2];
+        behind = behind || !(z > kMinDepth);
+        poly[i][0] = kPrincipal + kFocal * x / z;
+        poly[i][1] = kPrincipal + kFocal * y / z;
+        outside = outside || !(poly[i][0] >= kImageLo && poly[i][0] <= kImageHi && poly[i][1] >= kImageLo && poly[i][1] <= kImageHi);
+    }
+    if (behind) { u = v = NAN; return 0.0; }
+    int n = kDiscVerts;
+    const double (*P)[2] = poly;
+    if (clip && outside) {
+        n = clip_half_plane(poly, n, tmp, 0, kImageLo, -1.0);
+        n = clip_half_plane(tmp, n, poly, 0, kImageHi, 1.0);
+        n = clip_half_plane(poly, n, tmp, 1, kImageLo, -1.0);
+        n = clip_half_plane(tmp, n, poly, 1, kImageHi, 1.0);
+        if (n < 3) { u = v = NAN; return 0.0; }
+    }
+    // shoelace about the first vertex (keeps the cancellation small)
+    const double x0 = P[0][0], y0 = P[0][1];
+    double a2 = 0.0, cx = 0.0, cy = 0.0;
+    for (int i = 1; i + 1 < n; ++i) {
+        const double ax = P[i][0] - x0, ay = P[i][1] - y0, bx = P[i + 1][0] - x0, by = P[i + 1][1] - y0;
+        const double cr = ax * by - bx * ay;
+        a2 += cr;
+        cx += (ax + bx) * cr;
+        cy += (ay + by) * cr;
+    }
+    if (!(fabs(a2) > 1e-9)) { u = v = NAN; return 0.0; }
+    u = x0 + cx / (3.0 * a2);
+    v = y0 + cy / (3.0 * a2);
+    return 0.5 * fabs(a2);
+}
+
+// Feature coordinate `axis` (0 = u, 1 = v) of the target at pw under the configured plant: the projected centre (seen
+// from the offset sensor) or the disc centroid.  visible = false when the reference would measure NaN.
+UVS_DEV double scene_feature(const double (&sn)[6], const double (&cs)[6], const double* pw, const uvs_closed_loop_cfg& cfg,
+                             int axis, double& depth, bool& visible) {
+    if (cfg.disc_radius > 0.0) {
+        double u, v;
+        const double area = disc_centroid(sn, cs, pw, cfg.sensor_offset, cfg.disc_radius, cfg.fov_check != 0, u, v, depth);
+        visible = area > 0.0;
+        return axis ? v : u;
+    }
+    double pc[3];
+    ur10_point_in_camera(sn, cs, pw, pc);
+#pragma unroll
+    for (int j = 0; j < 3; ++j) pc[j] -= cfg.sensor_offset[j];
+    depth = pc[2];
+    const double f = kPrincipal + kFocal * (axis ? pc[1] : pc[0]) / pc[2];
+    visible = (f >= 0.0 && f < kResolution && depth > kMinDepth);
+    return f;
+}
+
+__host__ __device__ inline bool scene_plant(const uvs_closed_loop_cfg& cfg) {
+    return cfg.disc_radius > 0.0 || cfg.sensor_offset[0] != 0.0 || cfg.sensor_offset[1] != 0.0 || cfg.sensor_offset[2] != 0.0 ||
+           cfg.servo_substeps > 0;
+}
+
 // sin / cos of the six DH thetas for a group of GS lanes that all hold the same q: the evaluations are
 // split over the lanes of the group and exchanged with shuffles; gl = lane index in the group.  Every
 // lane of the warp must call.

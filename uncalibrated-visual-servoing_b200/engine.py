@@ -167,7 +167,8 @@ def start_poses(q_start, pose_seed, change_q_start, trial0, B, device="cuda"):
 
 def closed_loop_cfg(filt, noise, *, T, dt, ibvs_gain, q_start, desired_f, targets=None, initial_guess=True,
                     change_q_start=True, fov_check=False, pose_seed=12345, sweep=None, sweep_epoch=1,
-                    sweep_param=0, P0=None, v_max=0.0, a_max=0.0, servo_gain=0.0, trial_stride=1):
+                    sweep_param=0, P0=None, v_max=0.0, a_max=0.0, servo_gain=0.0, trial_stride=1,
+                    sensor_offset=None, disc_radius=0.0, servo_substeps=0, servo_kp=0.0):
     cfg = L.ClosedLoopCfg()
     cfg.filt = filt
     cfg.noise = noise
@@ -193,6 +194,10 @@ def closed_loop_cfg(filt, noise, *, T, dt, ibvs_gain, q_start, desired_f, target
     cfg._keep = (filt, dev(P0))
     cfg.P0 = _ptr(cfg._keep[1]).value
     cfg.v_max, cfg.a_max, cfg.servo_gain = float(v_max), float(a_max), float(servo_gain)   # servo model (0 = kinematic plant)
+    # scene plant (include/uvs_b200.h): sensor mount offset, finite discs, sub-stepped position servo; all 0 = off
+    for i, v in enumerate(sensor_offset if sensor_offset is not None else (0.0, 0.0, 0.0)):
+        cfg.sensor_offset[i] = float(v)
+    cfg.disc_radius, cfg.servo_kp, cfg.servo_substeps = float(disc_radius), float(servo_kp), int(servo_substeps)
     return cfg
 
 

@@ -61,6 +61,11 @@ class _Common:
         self.v_max = float(method_params.get("v_max", 0.0))
         self.a_max = float(method_params.get("a_max", 0.0))
         self.servo_gain = float(method_params.get("servo_gain", 0.0))
+        # additive: the scene plant (sensor mount offset, finite discs, sub-stepped position servo), include/uvs_b200.h
+        self.plant = dict(sensor_offset=method_params.get("sensor_offset"),
+                          disc_radius=float(method_params.get("disc_radius", 0.0)),
+                          servo_substeps=int(method_params.get("servo_substeps", 0)),
+                          servo_kp=float(method_params.get("servo_kp", 0.0)))
         self.P0, self.Q, self.R = (method_params.get(k) for k in ("P0", "Q", "R"))
 
     def _filter_params(self, nf):
@@ -112,7 +117,7 @@ class Experiment(_Common):
         cfg = engine.closed_loop_cfg(self._filter_params(nf), nparams, T=T, dt=self.t_s, ibvs_gain=self.ibvs_gain,
                                      q_start=self.q_start, desired_f=self.desired_f, targets=targets,
                                      initial_guess=self.initial_guess, change_q_start=False,
-                                     fov_check=self.fov_check, P0=self.P0, v_max=self.v_max, a_max=self.a_max, servo_gain=self.servo_gain)
+                                     fov_check=self.fov_check, P0=self.P0, v_max=self.v_max, a_max=self.a_max, servo_gain=self.servo_gain, **self.plant)
         out = engine.closed_loop(cfg, trial, 1, want_log=True, noise_in=noise_in,
                                  q0_in=engine.dev(np.asarray(self.q_start, dtype=float).reshape(1, 6)))
         k = int(out["frames"][0].item())
@@ -170,7 +175,7 @@ class BatchExperiment(_Common):
                                       targets=self.targets, initial_guess=self.initial_guess,
                                       change_q_start=self.change_q_start, fov_check=self.fov_check,
                                       pose_seed=self.pose_seed, sweep=self.sweep, sweep_epoch=self.sweep_epoch,
-                                      sweep_param=self.sweep_param, P0=self.P0, v_max=self.v_max, a_max=self.a_max, servo_gain=self.servo_gain)
+                                      sweep_param=self.sweep_param, P0=self.P0, v_max=self.v_max, a_max=self.a_max, servo_gain=self.servo_gain, **self.plant)
 
     def run(self, want_log=False, want_state=False, to_host=True, **kw):
         out = engine.closed_loop(self.config(), self.trial0, self.n_trials, want_log=want_log,

@@ -59,13 +59,15 @@ def load_config(config):
             raise ConfigError(1)
         run["method"] = Method[est["method"]]
         run["method_params"] = dict(est["estimator_params"])
-        # additive, optional: "plant": {"servo_gain": .., "v_max": .., "a_max": ..} (include/uvs_b200.h); absent = the
+        # additive, optional: "plant": {"servo_gain", "v_max", "a_max", "sensor_offset", "disc_radius", "servo_substeps",
+        # "servo_kp", "fov_check"} (include/uvs_b200.h: the servo limits and the scene plant); absent = the
         # kinematic plant q <- q + dq dt of experiment.py:320,335
         for key, val in config.get("plant", {}).items():
-            if key not in ("servo_gain", "v_max", "a_max"):
+            if key not in ("servo_gain", "v_max", "a_max", "sensor_offset", "disc_radius", "servo_substeps", "servo_kp",
+                           "fov_check"):
                 log.critical("Plant parameter " + str(key) + " unknown.")
                 raise ConfigError(1)
-            run["method_params"][key] = float(val)
+            run["method_params"][key] = val if isinstance(val, (list, tuple, bool)) else float(val)
         if nz["type"] not in NoiseType.__members__:
             log.critical("Noise type " + str(nz["type"]) + " unknown.")
             raise ConfigError(1)
