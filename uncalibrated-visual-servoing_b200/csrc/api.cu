@@ -251,6 +251,7 @@ int uvs_closed_loop(const uvs_closed_loop_cfg* cfg, uint64_t trial0, int64_t B,
     if (mode < 0) return set_error(UVS_ERR_INVALID, "UVS_MODE_BLOCKDIAG needs Q = R = P0 = NULL");
     ClosedLoopArgs a{};
     a.cfg = *cfg; a.io = *io; a.trial0 = trial0; a.B = B;
+    a.stride = cfg->trial_stride > 1 ? (unsigned long long)cfg->trial_stride : 1ull;
 #ifdef UVS_PHASE_CLOCKS
     a.phase_clk = phase_clk_buffer();
 #endif

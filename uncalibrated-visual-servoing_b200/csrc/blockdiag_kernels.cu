@@ -289,7 +289,7 @@ __global__ void __launch_bounds__(128, UVS_BD_MINB) bd_closed_loop_kernel(const 
         const bool trial_ok = b < a.B;
         const bool own = trial_ok && (gl < M);
         const long long bb = trial_ok ? b : 0;
-        const uint64_t trial = a.trial0 + (uint64_t)bb * (uint64_t)(cfg.trial_stride > 1 ? cfg.trial_stride : 1);
+        const uint64_t trial = a.trial0 + (uint64_t)bb * a.stride;
         double rho = cfg.noise.rho, alpha = cfg.noise.alpha;
         if (cfg.sweep_len > 0 && cfg.sweep_param != 0) {
             long long lvl = (long long)(trial / (uint64_t)(cfg.sweep_epoch > 0 ? cfg.sweep_epoch : 1));

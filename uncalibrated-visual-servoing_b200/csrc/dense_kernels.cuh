@@ -126,7 +126,7 @@ __global__ void UVS_DENSE_BOUNDS dense_closed_loop_kernel(const __grid_constant_
     DenseWS<M, MCKF>& w = wsv[warp];
 
     for (long long b = (long long)blockIdx.x * wpc + warp; b < a.B; b += (long long)gridDim.x * wpc) {
-        const uint64_t trial = a.trial0 + (uint64_t)b * (uint64_t)(cfg.trial_stride > 1 ? cfg.trial_stride : 1);
+        const uint64_t trial = a.trial0 + (uint64_t)b * a.stride;
         // noise level of this trial (main.py:121-127)
         double rho = cfg.noise.rho, alpha = cfg.noise.alpha;
         if (cfg.sweep_len > 0 && cfg.sweep_param != 0) {
@@ -221,7 +221,7 @@ __global__ void UVS_DENSE_BOUNDS dense_closed_loop_kernel(const __grid_constant_
             }
             __syncwarp();
             double f_true = 0.0, depth = 1.0;
-            bool visible = true;
+            [[maybe_unused]] bool visible = true;      // general instantiation only (scene plant); FAST tests the bounds directly
             if (lane < M) {
                 double sn[6], cs[6], pc[3];
 #pragma unroll
@@ -229,9 +229,11 @@ __global__ void UVS_DENSE_BOUNDS dense_closed_loop_kernel(const __grid_constant_
                     const double2 t = *reinterpret_cast<const double2*>(w.sc + 2 * j);
                     sn[j] = t.x; cs[j] = t.y;
                 }
-                bool scene = false;
-                if constexpr (!FAST) scene = scene_plant(cfg);
-                if (scene) {
+                if constexpr (FAST) {
+                    ur10_point_in_camera(sn, cs, target, pc);
+                    f_true = kPrincipal + fast_div(kFocal * ((lane & 1) ? pc[1] : pc[0]), pc[2]);    // pixel_of()
+                    depth = pc[2];
+                } else if (scene_plant(cfg)) {
                     f_true = scene_feature(sn, cs, target, cfg, lane & 1, depth, visible);
                 } else {
                     ur10_point_in_camera(sn, cs, target, pc);
@@ -241,7 +243,9 @@ __global__ void UVS_DENSE_BOUNDS dense_closed_loop_kernel(const __grid_constant_
                 }
             }
             if (cfg.fov_check) {
-                const bool bad = (lane < M) && !visible;
+                bool bad;
+                if constexpr (FAST) bad = (lane < M) && !(f_true >= 0.0 && f_true < kResolution && depth > kMinDepth);
+                else bad = (lane < M) && !visible;
                 if (__any_sync(UVS_FULL_MASK, bad)) {                   // NaN centroid -> FAIL
                     status = UVS_STATUS_FAIL; flags_all |= UVS_FLAG_OUT_OF_VIEW; break;
                 }
@@ -317,9 +321,11 @@ __global__ void UVS_DENSE_BOUNDS dense_closed_loop_kernel(const __grid_constant_
             if (a.io.dq_in && lane < 6) dq_l = a.io.dq_in[((size_t)b * T + k) * 6 + lane];     // replay gate: recorded command
             if (lane < 6) {                                              // experiment.py:320,335
                 w.dq[lane] = dq_l;
-                bool substepped = false;
-                if constexpr (!FAST) substepped = cfg.servo_substeps > 0;
-                if (substepped) {
+                if constexpr (FAST) {
+                    double v = dq_l;
+                    if (servo) { v = servo_rate(cfg, dq_l, v_prev); v_prev = v; }
+                    w.q[lane] = q_l + v * cfg.dt;
+                } else if (cfg.servo_substeps > 0) {
                     double qn = q_l;
                     servo_substepped(cfg, dq_l, qn, v_prev);
                     w.q[lane] = qn;

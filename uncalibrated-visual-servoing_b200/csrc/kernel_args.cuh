@@ -24,6 +24,7 @@ struct ClosedLoopArgs {
     uvs_closed_loop_io io;
     unsigned long long trial0;
     long long B;
+    unsigned long long stride;         // global trial of batch entry b = trial0 + b * stride (cfg.trial_stride, >= 1)
 #ifdef UVS_PHASE_CLOCKS
     unsigned long long* phase_clk;     // profiling build: device array of UVS_NPHASE totals
 #endif
