@@ -45,15 +45,17 @@ def published_tables(path):
 
 
 # published series -> (method, kernel_bw, annealing) ; figure -> random start poses?
+_R1 = {"KF": (2, 10.0, False), "RMCKF": (5, 10.0, True), "MCKF": (3, 10.0, True), "IMCC-KF": (4, 10.0, True)}
 SERIES = {
-    # results1: of {fixed, random start} x {annealing on, off} the fixed start pose with annealing is the closest on every
-    # series (means within 1.0-1.3x, smaller spread than results2 as published); without annealing RMCKF / IMCC-KF sit at 2x
-    "results1": dict(change_q_start=False, runs={"KF": (2, 10.0, False), "RMCKF": (5, 10.0, True),
-                                                 "MCKF": (3, 10.0, True), "IMCC-KF": (4, 10.0, True)}),
-    "results2": dict(change_q_start=True, runs={"KF": (2, 10.0, False), "RMCKF": (5, 10.0, True),
-                                                "MCKF": (3, 10.0, True), "IMCC-KF": (4, 10.0, True)}),
-    "results3": dict(change_q_start=True, runs={"KF": (2, 10.0, False), "RMCKF (Annealing)": (5, 10.0, True),
-                                                "RMCKF (σ = 1)": (5, 1.0, False), "RMCKF (σ = 10)": (5, 10.0, False)}),
+    # results1: the .fig does not say what produced it.  Round 1 took it for the fixed start pose (smaller spread at alpha = 2
+    # than results2).  The scene decode of round 2 rules that out for config.json's q_start: there the green disc (radius
+    # 0.0375 m) is ENTIRELY outside the image, the detector returns NaN and every experiment fails (the scene-plant rows
+    # below show 100 % failures).  So results1 also had perturbed start poses; both readings are reported.
+    "results1 (read as: fixed start pose)": dict(fig="results1", change_q_start=False, runs=_R1),
+    "results1 (read as: random start poses)": dict(fig="results1", change_q_start=True, runs=_R1),
+    "results2": dict(fig="results2", change_q_start=True, runs=_R1),
+    "results3": dict(fig="results3", change_q_start=True, runs={"KF": (2, 10.0, False), "RMCKF (Annealing)": (5, 10.0, True),
+                                                                 "RMCKF (σ = 1)": (5, 1.0, False), "RMCKF (σ = 10)": (5, 10.0, False)}),
 }
 
 
@@ -71,6 +73,9 @@ def run_series(uvs, method, kernel_bw, annealing, change_q_start, epoch, limits)
     res = []
     for lvl in range(len(ALPHAS)):
         v = itae[lvl][ok[lvl]]
+        if len(v) == 0:
+            res.append((float("nan"), float("nan"), float("nan"), int((~ok[lvl]).sum())))
+            continue
         res.append((float(v.mean()), float(v.std()), float(np.median(v)), int((~ok[lvl]).sum())))
     return res
 
@@ -78,24 +83,35 @@ def run_series(uvs, method, kernel_bw, annealing, change_q_start, epoch, limits)
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--epoch", type=int, default=4000)
-    ap.add_argument("--out", default=os.path.join(ROOT, "profiles", "r01_itae_vs_published.md"))
+    ap.add_argument("--out", default=os.path.join(ROOT, "profiles", "r02_itae_vs_published.md"))
     a = ap.parse_args()
     import uvs_b200 as uvs
     pub = published_tables(os.path.join(ROOT, "BASELINE.md"))
     # servo lag: the scenes' joints are position-controlled with P-gain 0.1 at a 5 ms dynamics step, i.e.
     # a joint covers 1 - 0.9^10 = 0.651 of the commanded step within one 50 ms frame
+    # scene plant (round 2): the sensor sits ~(0, 0.007, 0.014) m off DH frame 6, the targets are discs of
+    # 0.0375 m radius whose visible-region centroid is the feature (clipped to the image; a trial fails only when a disc is
+    # entirely out of view), the joints follow a P servo (gain 0.1) at the 5 ms dynamics step under 60 deg/s, 360 deg/s^2
+    discs = dict(sensor_offset=(0.0, 0.007, 0.014), disc_radius=0.0375, fov_check=True)
     plants = {"kinematic": {}, "first-order servo lag (servo_gain = 1 - 0.9^10 = 0.651)": dict(servo_gain=1.0 - 0.9 ** 10),
-              "servo limits (60 deg/s, 360 deg/s^2)": dict(v_max=1.0472, a_max=6.283)}
+              "servo limits (60 deg/s, 360 deg/s^2)": dict(v_max=1.0472, a_max=6.283),
+              "scene plant: offset sensor + finite discs clipped to the image, kinematic joints": dict(discs),
+              "scene plant: offset sensor + finite discs + sub-stepped P servo (kp 0.1 x 10, 60 deg/s, 360 deg/s^2)":
+                  dict(discs, servo_substeps=10, servo_kp=0.1, v_max=1.0472, a_max=6.283)}
     md = ["# Closed-loop ITAE: this engine vs the reference's published curves", "",
           f"`python tools/published_comparison.py --epoch {a.epoch}` on one B200.  Published = mean ± std of 100 CoppeliaSim "
           "experiments per level, decoded from `results/results{1,2,3}.fig` (BASELINE.md §1).  Ours = mean ± std "
           f"(median) of {a.epoch} kinematic-plant trials per level, alpha-stable noise, 4 features, T = 300; which "
-          "config produced each figure is inferred (BASELINE.md; the .fig files do not say): results1 = fixed start pose, "
-          "results2 / results3 = random start poses, annealing on the correntropy filters in all three.  ratio = ours / published mean.", ""]
+          "config produced each figure is inferred (BASELINE.md; the .fig files do not say): results2 / results3 = random start "
+          "poses; results1 is reported under both readings (fixed / random start pose); annealing on the correntropy filters in "
+          "all three.  ratio = ours / published mean.  Plants: the ideal kinematic point-feature plant, its servo variants of "
+          "round 1, and the scene plant of round 2 (include/uvs_b200.h: sensor offset, finite discs with image clipping, "
+          "sub-stepped position servo; constants decoded from scenarios/*.ttt).", ""]
     summary = []
-    for fig, spec in SERIES.items():
+    for label, spec in SERIES.items():
+        fig = spec["fig"]
         for plant, limits in plants.items():
-            md += [f"## {fig} — {plant}", "", "| α | " + " | ".join(f"{n}: published | ours | ratio" for n in spec["runs"]) + " |",
+            md += [f"## {label} — {plant}", "", "| α | " + " | ".join(f"{n}: published | ours | ratio" for n in spec["runs"]) + " |",
                    "|---|" + "---|---|---|" * len(spec["runs"])]
             cols = {}
             for name, (method, bw, anneal) in spec["runs"].items():
@@ -105,18 +121,20 @@ def main():
                 for name in spec["runs"]:
                     pm, ps = pub[fig][name][lvl]
                     om, osd, omed, nfail = cols[name][lvl]
-                    cells.append(f"{pm:.0f} ± {ps:.0f} | {om:.0f} ± {osd:.0f} ({omed:.0f}) | {om / pm:.2f}")
+                    cells.append(f"{pm:.0f} ± {ps:.0f} | {om:.0f} ± {osd:.0f} ({omed:.0f}) | {om / pm:.2f}" if om == om else
+                                 f"{pm:.0f} ± {ps:.0f} | all {nfail} trials FAIL | –")
                 md.append(f"| {alpha:.4f} | " + " | ".join(cells) + " |")
             md.append("")
             for name in spec["runs"]:
                 r = np.array([cols[name][lvl][0] / pub[fig][name][lvl][0] for lvl in range(len(ALPHAS))])
                 # alpha >= 1.18: beyond the two most impulsive levels, whose published means are dominated by a few samples
-                summary.append((fig, plant, name, float(np.exp(np.mean(np.log(r[2:])))), float(r[2:].min()), float(r[2:].max()),
-                                float(r[0]), float(r[1])))
+                nfail = sum(cols[name][lvl][3] for lvl in range(len(ALPHAS)))
+                summary.append((label, plant, name, float(np.exp(np.mean(np.log(r[2:])))), float(r[2:].min()), float(r[2:].max()),
+                                float(r[0]), float(r[1]), nfail / (a.epoch * len(ALPHAS))))
     md += ["## Summary: ours / published mean ITAE", "",
-           "| figure | plant | series | geometric mean, α ≥ 1.18 | min | max | α = 1.00 | α = 1.09 |", "|---|---|---|---|---|---|---|---|"]
+           "| figure | plant | series | geometric mean, α ≥ 1.18 | min | max | α = 1.00 | α = 1.09 | failed trials |", "|---|---|---|---|---|---|---|---|---|"]
     for s in summary:
-        md.append(f"| {s[0]} | {s[1]} | {s[2]} | {s[3]:.2f} | {s[4]:.2f} | {s[5]:.2f} | {s[6]:.2f} | {s[7]:.2f} |")
+        md.append(f"| {s[0]} | {s[1]} | {s[2]} | {s[3]:.2f} | {s[4]:.2f} | {s[5]:.2f} | {s[6]:.2f} | {s[7]:.2f} | {s[8]:.3f} |")
     md.append("")
     with open(a.out, "w", encoding="utf-8") as fh:
         fh.write("\n".join(md) + "\n")
