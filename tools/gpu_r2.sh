@@ -30,6 +30,17 @@ try:
 except Exception as e: print("$(basename $lib)", "FAILED", e)
 PY
     done ;;
+bdvariants)
+    for lib in uncalibrated-visual-servoing_b200/libuvs_b200*.so; do
+        UVS_B200_LIB=$PWD/$lib timeout 300 python bench.py --mode blockdiag --steps 5 --warmup 3 --no-cpu-baseline --no-extras --no-blockdiag-extra \
+            > $O/bd_$(basename $lib .so).json 2> $O/bd_$(basename $lib .so).err
+        python - <<PY
+import json
+try:
+    d=json.load(open("$O/bd_$(basename $lib .so).json")); print("blockdiag $(basename $lib)", "%.4g"%d["value"], "kernel_ms %.2f"%d["roofline"]["kernel_ms"])
+except Exception as e: print("$(basename $lib)", "FAILED", e)
+PY
+    done ;;
 ncu)
     timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $O/launches.csv \
         python bench.py --steps 2 --warmup 1 --no-cpu-baseline > $O/bench_under_ncu.log 2>&1

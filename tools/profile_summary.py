@@ -79,6 +79,18 @@ def main():
                                            f"{traffic['dense_executed_flops_per_filter_step']:.0f} | flop |")
                 except (ValueError, KeyError):
                     pass
+            if rep == "bd_full":
+                # the block-diagonal family's OWN executed flop count (never F_alg): bench-sized launch, 100 000 x 300 steps
+                try:
+                    per_cycle = sum(k * float(v[hdr.index(f"smsp__sass_thread_inst_executed_op_{op}_pred_on.sum.per_cycle_elapsed")])
+                                    for op, k in (("dfma", 2.0), ("dmul", 1.0), ("dadd", 1.0)))
+                    cycles = float(v[hdr.index("smsp__cycles_elapsed.max")]) if "smsp__cycles_elapsed.max" in hdr \
+                        else float(v[hdr.index("sm__cycles_elapsed.max")])
+                    traffic["blockdiag_executed_flops_per_filter_step"] = per_cycle * cycles / (100000 * 300)
+                    md.insert(len(md) - 1, f"| executed FP64 flops per filter-step (2 dfma + dmul + dadd) | "
+                                           f"{traffic['blockdiag_executed_flops_per_filter_step']:.0f} | flop |")
+                except (ValueError, KeyError):
+                    pass
             ir, iw = hdr.index("dram__bytes_read.sum"), hdr.index("dram__bytes_write.sum")
             if rep not in ("dense_full", "twist_full"):            # bench-sized launches only
                 key = ("dense" if "dense" in name else "bd") + "_closed_loop_kernel<8, GMCKF>"

@@ -273,8 +273,14 @@ template <int M, int METHOD, bool EXTRAS>
 __global__ void __launch_bounds__(128, UVS_BD_MINB) bd_closed_loop_kernel(const __grid_constant__ ClosedLoopArgs a) {
     constexpr int GS = GroupSize<M>::value, GPW = 32 / GS, N = 6 * M, LOGW = 6 + 2 * M;
     constexpr int WPC = 4;
-    __shared__ __align__(16) double sJ[WPC][GPW][M * 6];
-    __shared__ __align__(16) double sSc[WPC][GPW][56];
+    // per-group strides chosen so that the GPW groups of a warp start 8 banks apart (x 4-byte banks, mod 32): with the
+    // natural strides (48 / 56 doubles = 0 / 16 banks mod 32) the groups' identical access patterns collided 2-4 ways
+#ifndef UVS_BD_PAD
+#define UVS_BD_PAD 1
+#endif
+    constexpr int JS = M * 6 + ((UVS_BD_PAD && M == 8) ? 4 : 0), SS = 56 + (UVS_BD_PAD ? 4 : 0);
+    __shared__ __align__(16) double sJ[WPC][GPW][JS];
+    __shared__ __align__(16) double sSc[WPC][GPW][SS];
     __shared__ __align__(16) double sBig[(M >= 6) ? WPC : 1][(M >= 6) ? GPW : 1][(M >= 6) ? pinv_scratch_doubles(M) : 2];   // Jacobi fallback work matrices
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, gl = lane % GS, grp = lane / GS;
     const long long warp_id = (long long)blockIdx.x * WPC + warp;
