@@ -270,7 +270,7 @@ int uvs_twist_loop(const uvs_closed_loop_cfg* cfg, const uvs_twist_cfg* tw, uint
  * frames_host [B]): runs on the calling thread's cudaStreamPerThread, copies the
  * results back (a DMA when the buffers are page-locked) and synchronises.  The
  * device-side result scratch is owned by the library: one block per host thread and device
- * that only grows (32 B per trial) and lives until the thread exits. */
+ * that only grows (32 B per trial) and is freed when that host thread exits. */
 int uvs_closed_loop_host(const uvs_closed_loop_cfg* cfg, uint64_t trial0, int64_t B,
                          double* stats_host, int32_t* status_host, int32_t* frames_host);
 

@@ -50,6 +50,9 @@ ncu)
         python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-blockdiag-extra --no-extras > $O/ncu_dense_100k.log 2>&1
     timeout 900 ncu --set full --clock-control none --import-source on -k regex:bd_closed_loop -c 1 -o $O/bd_full -f \
         python bench.py --steps 1 --warmup 1 --mode blockdiag --no-cpu-baseline --no-blockdiag-extra --no-extras > $O/ncu_bd.log 2>&1
-    ls -la $O ;;
+    # the reports are too large to travel back (64 MiB cap): summarise here, keep the summaries only
+    python tools/profile_summary.py $TAG ${TAG} $O/profiles > $O/profile_summary.log 2>&1; tail -2 $O/profile_summary.log
+    ls -la $O | head -30
+    rm -f $O/*.ncu-rep ;;
 esac
 done

@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Turns the scratch ncu reports of one GPU round (gpurun_out/<tag>/) into the committed summaries under profiles/:
 
-    python tools/profile_summary.py <tag> <round-label>
+    python tools/profile_summary.py <tag> <round-label> [out-dir]
 
   profiles/<label>_launches.csv          ncu launch list of `bench.py --steps 2 --warmup 1`
   profiles/<label>_ncu_full_summary.md   key counters of the `ncu --set full` captures (dense + block-diagonal kernels)
@@ -43,7 +43,9 @@ def to_bytes(v, unit):
 def main():
     tag, label = sys.argv[1], sys.argv[2]
     src = os.path.join(ROOT, "gpurun_out", tag)
-    dst = os.path.join(ROOT, "profiles")
+    # run ON the GPU box (the .ncu-rep files are too large to travel back): third argument = output directory
+    dst = sys.argv[3] if len(sys.argv) > 3 else os.path.join(ROOT, "profiles")
+    os.makedirs(dst, exist_ok=True)
     md = [f"# {label}: `ncu --set full --clock-control none` counters (B200, sm_100a)", "",
           "Raw reports stay in gpurun_out/ (scratch).  Per-launch times under ncu are serialised and cold-cache: "
           "compare shares, not absolutes; the bench line's own CUDA-event timing is in the *_bench.json beside this file.", ""]

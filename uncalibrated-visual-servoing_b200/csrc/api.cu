@@ -309,7 +309,14 @@ int uvs_closed_loop_host(const uvs_closed_loop_cfg* cfg, uint64_t trial0, int64_
     // and the call ends with one stream synchronisation
     const size_t n_stats = sizeof(double) * 3 * (size_t)B, n_i32 = sizeof(int32_t) * (size_t)B;
     cudaStream_t st = cudaStreamPerThread;
-    struct Scratch { unsigned char* p = nullptr; size_t cap = 0; };
+    struct Scratch {
+        unsigned char* p = nullptr; size_t cap = 0; int dev = -1;
+        ~Scratch() {                                            // the owning host thread exits: give the block back
+            if (!p) return;
+            int cur = 0;
+            if (cudaGetDevice(&cur) == cudaSuccess && cudaSetDevice(dev) == cudaSuccess) { cudaFree(p); cudaSetDevice(cur); }
+        }
+    };
     constexpr int kMaxDevices = 64;
     static thread_local Scratch per_device[kMaxDevices];       // one block per (host thread, device)
     int dev = 0;
@@ -319,9 +326,9 @@ int uvs_closed_loop_host(const uvs_closed_loop_cfg* cfg, uint64_t trial0, int64_
     Scratch& sc = per_device[dev];
     if (sc.cap < n_stats + 2 * n_i32) {
         if (sc.p) cudaFree(sc.p);
-        sc = Scratch{};
+        sc.p = nullptr; sc.cap = 0; sc.dev = dev;
         rc = check_cuda(cudaMalloc((void**)&sc.p, n_stats + 2 * n_i32), "cudaMalloc result scratch");
-        if (rc) { sc = Scratch{}; return rc; }
+        if (rc) { sc.p = nullptr; return rc; }
         sc.cap = n_stats + 2 * n_i32;
     }
     unsigned char* scratch = sc.p;
