@@ -124,7 +124,7 @@ __global__ void __launch_bounds__(kTwistThreads, 2) twist_closed_loop_kernel(con
                 u = project_coord(T6, target, 0, depth);
                 v = project_coord(T6, target, 1, depth);
                 zc = (tw.depth_mode == UVS_DEPTH_HEIGHT) ? T6.p[2] : camera_distance(T6, target);
-                if (scene_plant(cfg)) {
+                if (!FAST && scene_plant(cfg)) {
                     double sn0[6], cs0[6];
                     bool vis;
 #pragma unroll
@@ -186,7 +186,8 @@ __global__ void __launch_bounds__(kTwistThreads, 2) twist_closed_loop_kernel(con
             double zax[3], org[3];
             double f_scene = 0.0, depth_scene = 1.0;
             bool vis_scene = true;
-            const bool scene = scene_plant(cfg);
+            bool scene = false;                                            // scene plant: general instantiation only
+            if constexpr (!FAST) scene = scene_plant(cfg);
             {
                 double sn[6], cs[6];
 #pragma unroll
@@ -195,7 +196,9 @@ __global__ void __launch_bounds__(kTwistThreads, 2) twist_closed_loop_kernel(con
                     sn[j] = t.x; cs[j] = t.y;
                 }
                 ur10_chain_columns(sn, cs, lane, T6, zax, org);
-                if (scene && lane < M) f_scene = scene_feature(sn, cs, target, cfg, lane & 1, depth_scene, vis_scene);
+                if constexpr (!FAST) {
+                    if (scene && lane < M) f_scene = scene_feature(sn, cs, target, cfg, lane & 1, depth_scene, vis_scene);
+                }
             }
             // tw.stale_fk: the scripts that never refresh UR10Simulation's cached transforms inside the loop keep the
             // start pose's J_geom and R06 (kalman_4_features.py:165-169; frame 0 is at the start pose)
@@ -318,7 +321,7 @@ __global__ void __launch_bounds__(kTwistThreads, 2) twist_closed_loop_kernel(con
 #pragma unroll
             for (int r = 0; r < 6; ++r) {
                 if (lane == r) w.dq[r] = dp[r];
-                if (cfg.servo_substeps > 0) {
+                if (!FAST && cfg.servo_substeps > 0) {
                     servo_substepped(cfg, dq[r], q[r], v_prev[r]);
                 } else {
                     double v = dq[r];
@@ -369,7 +372,7 @@ static cudaError_t twist_launch(Kernel kernel, const TwistArgs& a, size_t smem, 
     template <int METHOD> static cudaError_t twist_one_##MM(const TwistArgs& a, int sms, cudaStream_t st) {     \
         const uvs_filter_params& fp = a.cfg.filt;                                                                \
         constexpr bool CAN_FAST = METHOD != UVS_METHOD_MCKF && METHOD != UVS_METHOD_ANALYTICAL;                  \
-        if (CAN_FAST && fp.Q == nullptr && fp.R == nullptr && fp.joseph)                                         \
+        if (CAN_FAST && fp.Q == nullptr && fp.R == nullptr && fp.joseph && !scene_plant(a.cfg))                  \
             return twist_launch(twist_closed_loop_kernel<MM, METHOD, CAN_FAST>, a,                               \
                                 twist_smem_bytes<MM, METHOD == UVS_METHOD_MCKF>(kTwistWarps), sms, st);          \
         return twist_launch(twist_closed_loop_kernel<MM, METHOD, false>, a,                                      \
