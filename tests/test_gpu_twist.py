@@ -246,3 +246,26 @@ def test_twist_loop_scene_plant(uvs):
         assert int(out["frames"][b]) == k
         assert rel_err(log[b, :k, :6], ref["q_log"]) <= 1e-8
         assert rel_err(log[b, :k, 6:14], ref["f_log"]) <= 1e-8
+
+
+@pytest.mark.parametrize("name", ["kalman_4_features", "mckf_1_feature", "mckf_3_features", "mckf_4_features"])
+def test_twist_kernel_state_every_frame(uvs, name):
+    """The per-frame trace of uvs_twist_loop against the X_log the unmodified scripts recorded: the estimated Jacobian of
+    EVERY frame within the per-step tolerance (kalman_4_features runs the FAST instantiation with the covariance update
+    inside the pseudo-inverse — twist_closed_loop_kernel<8, KF, FAST>; the mckf_* scripts the general one)."""
+    L, E = uvs._lib, uvs.engine
+    g = load_golden(f"ref_twist_{name}.npz")
+    ocfg = twist_cfg_from_golden(g)
+    nf, T, k = int(g["nf"]), int(g["T"]), int(g["frames"])
+    m = 2 * nf
+    cfg, tw = gpu_cfg(uvs, ocfg)
+    noise = np.zeros((1, T, m))
+    noise[0, :k] = g["noise_log"]
+    X0 = E.dev(g["x0"][None]) if "x0" in g else None
+    out = E.twist_loop(cfg, tw, 0, 1, want_trace=True, p_layout=L.P_DENSE, noise_in=E.dev(noise), X0_in=X0)
+    assert int(out["frames"][0]) == k
+    X_log = out["X_log"].cpu().numpy()[0, :k]
+    tol = TOL_BY_SCRIPT.get(name, (TOL, TOL))[1]
+    err = [rel_err(X_log[i], g["X_log"][i]) for i in range(k)]
+    assert max(err) <= 10 * tol, (name, int(np.argmax(err)), max(err))
+    assert max(err[:50]) <= tol or name == "mckf_3_features", (name, max(err[:50]))
