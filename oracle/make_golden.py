@@ -16,7 +16,7 @@ Files written (all float64 unless noted):
   ref_dense_<name>.npz   same with general SPD P0/Q/R injected through a numpy proxy that
                          answers the reference's first three ``np.eye`` calls
                          (experiment.py:73,75,76); full P stored on ``p_frames``.
-  ref_stats_<name>.npz   ISE/IAE/ITAE of 64 reference closed-loop trials (random start poses).
+  ref_stats_<name>.npz   ISE/IAE/ITAE of 256 reference closed-loop trials (random start poses).
   ref_noise.npz          10 000 reference NoiseProfiler draws per distribution (for KS tests) and
                          a hold-logic trace produced with injected generators.
 """
@@ -198,8 +198,9 @@ def main():
     desired = np.array([149.0, 145.0, 125.0, 121.0, 101.0, 145.0, 125.0, 169.0])
     for name, method, mparams in (("kf_alpha15", "KF", dict(mp)),
                                   ("gmckf_alpha15_anneal", "GMCKF", dict(mp, annealing=True))):
-        st = np.zeros((64, 3)); status = np.zeros(64, dtype=np.int64); q0s = np.zeros((64, 6))
-        for i in range(64):
+        n_stat = 256
+        st = np.zeros((n_stat, 3)); status = np.zeros(n_stat, dtype=np.int64); q0s = np.zeros((n_stat, 6))
+        for i in range(n_stat):
             q0 = noise_model.start_pose(q_nom, 12345, i, True)
             q0[1] = min(q0[1], -0.15)          # keep every start pose inside the field of view
             res = run_reference(ref_experiment, ref_noise, method, "ALPHA_STABLE",

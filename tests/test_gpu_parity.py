@@ -527,7 +527,8 @@ def test_closed_loop_philox_matches_oracle(uvs, method, noise, min_full):
 
 def test_closed_loop_statistics_match_reference(uvs):
     """Distributional parity with the reference's closed loop (PCG64 noise, same start poses):
-    KS test on ISE / IAE / ITAE of 512 GPU trials vs 64 reference trials."""
+    KS test on ISE / IAE / ITAE of 2048 GPU trials vs 256 runs of the unmodified reference; medians within 5 %, the
+    quartiles of ITAE within 7 %."""
     from scipy import stats as sps
     L, E = uvs._lib, uvs.engine
     for name, method, anneal in (("kf_alpha15", 2, False), ("gmckf_alpha15_anneal", 5, True)):
@@ -540,10 +541,13 @@ def test_closed_loop_statistics_match_reference(uvs):
                                 desired_f=[149.0, 145.0, 125.0, 121.0, 101.0, 145.0, 125.0, 169.0])
         out = E.closed_loop(cfg, 0, len(q0), q0_in=E.dev(q0))
         st = out["stats"].cpu().numpy()[out["status"].cpu().numpy() == 0]
+        assert len(g["stats"]) == 256 and len(st) >= 2000
         for j in range(3):
             ks = sps.ks_2samp(st[:, j], g["stats"][:, j])
-            assert ks.pvalue > 1e-3, (name, j, ks)
-        assert abs(np.median(st[:, 2]) / np.median(g["stats"][:, 2]) - 1) < 0.1
+            assert ks.pvalue > 0.01, (name, j, ks)
+            assert abs(np.median(st[:, j]) / np.median(g["stats"][:, j]) - 1) < 0.05, (name, j)
+        for qq in (0.25, 0.75):
+            assert abs(np.quantile(st[:, 2], qq) / np.quantile(g["stats"][:, 2], qq) - 1) < 0.07, (name, qq)
 
 
 def test_reduce_stats(uvs):

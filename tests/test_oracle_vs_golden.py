@@ -133,17 +133,17 @@ def test_hold_logic_matches_reference():
 
 
 def test_closed_loop_statistics_match_reference():
-    """Oracle closed loop (Philox noise) vs 64 closed-loop runs of the reference
+    """Oracle closed loop (Philox noise) vs 256 closed-loop runs of the reference
     (PCG64 noise), same start poses: ITAE distributions must agree."""
     for name, method, anneal in (("kf_alpha15", filters.KF, False), ("gmckf_alpha15_anneal", filters.GMCKF, True)):
         g = load_golden(f"ref_stats_{name}.npz")
         cfg = closed_loop.make_cfg(method=method, annealing=anneal,
                                    noise_params=dict(alpha=1.5, beta=0.0, gamma=1.0, delta=0.0))
-        mine = np.array([closed_loop.run_trial(cfg, i, q0=g["q0"][i])["stats"] for i in range(0, 64, 2)])
+        mine = np.array([closed_loop.run_trial(cfg, i, q0=g["q0"][i])["stats"] for i in range(0, 256, 4)])
         for j in range(3):
             ks = sps.ks_2samp(mine[:, j], g["stats"][:, j])
-            assert ks.pvalue > 1e-3, (name, j, ks)
-        assert abs(np.median(mine[:, 2]) / np.median(g["stats"][:, 2]) - 1) < 0.15
+            assert ks.pvalue > 0.01, (name, j, ks)
+        assert abs(np.median(mine[:, 2]) / np.median(g["stats"][:, 2]) - 1) < 0.1
 
 
 # ---- camera-twist pipeline: the oracle against the reference's own tests/ scripts -----------------------------
