@@ -182,8 +182,9 @@ def test_published_tables_parse_and_servo_rate():
     from oracle import closed_loop as CL
     pub = pc.published_tables(os.path.join(ROOT, "BASELINE.md"))
     assert sorted(pub) == ["results1", "results2", "results3"]
-    for fig, series in pub.items():
-        assert set(series) == set(pc.SERIES[fig]["runs"]) and all(len(v) == 12 for v in series.values())
+    for spec in pc.SERIES.values():              # every reported series has its published column
+        series = pub[spec["fig"]]
+        assert set(series) == set(spec["runs"]) and all(len(v) == 12 for v in series.values())
     assert pub["results2"]["RMCKF"][0] == (233102.0, 355742.0) and pub["results3"]["RMCKF (σ = 1)"][11][0] == 238561.0
     cfg = dict(dt=0.05, v_max=1.0, a_max=4.0, servo_gain=0.5)
     v = CL.servo_rate(cfg, np.array([4.0, -0.1, 0.3]), np.array([0.0, 0.0, 0.2]))
