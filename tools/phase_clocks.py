@@ -23,6 +23,11 @@ NAMES = ["0 plant: sincos, point in camera, pixel", "1 noise (Philox alpha-stabl
          "11 frame tail: dq, finiteness, integrals, integrate"]
 
 
+QUAD_CHAIN = ["hold logic, innovation, kernel weights", "wait (1): A, S0", "S, L D L^T, S^-1", "wait (2)", "next frame's noise draw",
+              "wait (3): gain rows, X", "pseudo-inverse", "command, integrals, log, integrate", "plant of the next frame", "wait (4)"]
+QUAD_COV = ["predict, A, S0", "wait (1), (2): weights, S^-1", "gain rows, X, U", "wait (3)", "rank update", "wait (4): pinv ... plant"]
+
+
 def main():
     L, E = uvs._lib, uvs.engine
     lib = L.load()
@@ -36,15 +41,25 @@ def main():
                             desired_f=[149.0, 145.0, 125.0, 121.0, 101.0, 145.0, 125.0, 169.0], sweep=sweep,
                             sweep_epoch=B // 12 + 1, sweep_param=2)
     out = E.closed_loop(cfg, 0, B)
-    buf = (C.c_ulonglong * 12)()
+    buf = (C.c_ulonglong * 40)()
     fn(buf, 1)
     out = E.closed_loop(cfg, 0, B, out=out)
     fn(buf, 1)
     steps = int(out["frames"].sum().item())
-    tot = np.array(list(buf), dtype=float) / steps
-    print(f"{steps} filter-steps; per-warp cycles per filter-step: {tot.sum():.0f}")
-    for n, v in zip(NAMES, tot):
-        print(f"  {v:8.0f}  {100 * v / tot.sum():5.1f} %  {n}")
+    allc = np.array(list(buf), dtype=float)
+    tot = allc[:12] / steps
+    if tot.sum() > 0:
+        print(f"{steps} filter-steps; per-warp cycles per filter-step: {tot.sum():.0f}")
+        for n, v in zip(NAMES, tot):
+            print(f"  {v:8.0f}  {100 * v / tot.sum():5.1f} %  {n}")
+    if allc[12:].sum() > 0:          # the quad kernel (dense_quad.cuh): cycles per FRAME of a four-filter CTA, per role
+        frames = steps / 4.0
+        ch, cv = allc[12:22] / frames, allc[22:28] / (4.0 * frames)
+        print(f"quad kernel: {frames:.0f} CTA-frames; chain warp {ch.sum():.0f} cycles per frame, covariance warp {cv.sum():.0f}")
+        for n, v in zip(QUAD_CHAIN, ch):
+            print(f"  chain  {v:8.0f}  {100 * v / ch.sum():5.1f} %  {n}")
+        for n, v in zip(QUAD_COV, cv):
+            print(f"  covar  {v:8.0f}  {100 * v / cv.sum():5.1f} %  {n}")
 
 
 if __name__ == "__main__":

@@ -68,7 +68,7 @@ static int resolve_mode(const uvs_filter_params& fp, bool p_is_blocks_or_identit
 #ifdef UVS_PHASE_CLOCKS
 static unsigned long long* g_phase_clk = nullptr;      // device array, profiling build only
 static unsigned long long* phase_clk_buffer() {
-    if (!g_phase_clk) { cudaMalloc((void**)&g_phase_clk, sizeof(unsigned long long) * UVS_NPHASE); cudaMemset(g_phase_clk, 0, sizeof(unsigned long long) * UVS_NPHASE); }
+    if (!g_phase_clk) { cudaMalloc((void**)&g_phase_clk, sizeof(unsigned long long) * UVS_NPHASE_BUF); cudaMemset(g_phase_clk, 0, sizeof(unsigned long long) * UVS_NPHASE_BUF); }
     return g_phase_clk;
 }
 #endif
@@ -465,8 +465,8 @@ int uvs_reduce_stats(int64_t B, uint64_t trial0, int32_t trial_stride, int32_t s
 // profiling build only: read (and reset) the per-phase clock totals of the dense closed-loop kernel
 int uvs_debug_phase_clocks(unsigned long long* out_host, int reset) {
     cudaDeviceSynchronize();
-    if (out_host) cudaMemcpy(out_host, phase_clk_buffer(), sizeof(unsigned long long) * UVS_NPHASE, cudaMemcpyDeviceToHost);
-    if (reset) cudaMemset(phase_clk_buffer(), 0, sizeof(unsigned long long) * UVS_NPHASE);
+    if (out_host) cudaMemcpy(out_host, phase_clk_buffer(), sizeof(unsigned long long) * UVS_NPHASE_BUF, cudaMemcpyDeviceToHost);
+    if (reset) cudaMemset(phase_clk_buffer(), 0, sizeof(unsigned long long) * UVS_NPHASE_BUF);
     return 0;
 }
 #endif

@@ -362,6 +362,9 @@ __global__ void UVS_DENSE_BOUNDS dense_closed_loop_kernel(const __grid_constant_
     }
 }
 
+template <int M, int METHOD>
+static bool quad_try(const ClosedLoopArgs& a, int sms, cudaStream_t st, cudaError_t* err);      // dense_quad.cuh
+
 // host-side dispatch (defined once per M in dense_m*.cu): persistent grid = SMs x resident CTAs
 template <int M> cudaError_t launch_dense_replay(const ReplayArgs& a, int sms, cudaStream_t st);
 template <int M> cudaError_t launch_dense_closed_loop(const ClosedLoopArgs& a, int sms, cudaStream_t st);
@@ -392,10 +395,13 @@ static cudaError_t dense_launch(Kernel kernel, const Args& a, long long B, size_
     }                                                                                                        \
     template <int METHOD> static cudaError_t closed_one_##MM(const ClosedLoopArgs& a, int sms, cudaStream_t st) { \
         const uvs_filter_params& fp = a.cfg.filt;                                                            \
-        if (UVS_DENSE_FAST && fp.Q == nullptr && fp.R == nullptr && fp.joseph && !scene_plant(a.cfg))        \
+        if (UVS_DENSE_FAST && fp.Q == nullptr && fp.R == nullptr && fp.joseph && !scene_plant(a.cfg)) {      \
+            cudaError_t qe;                                                                                  \
+            if (quad_try<MM, METHOD>(a, sms, st, &qe)) return qe;      /* dense_quad.cuh: four filters per CTA */ \
             return dense_launch(dense_closed_loop_kernel<MM, METHOD, UVS_DENSE_FAST != 0>, a, a.B,           \
                                 dense_smem_bytes<MM, METHOD == UVS_METHOD_MCKF>(kDenseWarps) +               \
                                     sigma_table_bytes(a.cfg.T), sms, st);                                    \
+        }                                                                                                    \
         return dense_launch(dense_closed_loop_kernel<MM, METHOD, false>, a, a.B,                             \
                             dense_smem_bytes<MM, METHOD == UVS_METHOD_MCKF>(kDenseWarps) +                   \
                                 sigma_table_bytes(a.cfg.T), sms, st);                                        \
