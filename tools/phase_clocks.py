@@ -23,9 +23,9 @@ NAMES = ["0 plant: sincos, point in camera, pixel", "1 noise (Philox alpha-stabl
          "11 frame tail: dq, finiteness, integrals, integrate"]
 
 
-QUAD_CHAIN = ["hold logic, innovation, kernel weights", "wait (1): A, S0", "S, L D L^T, S^-1", "wait (2)", "next frame's noise draw",
-              "wait (3): gain rows, X", "pseudo-inverse", "command, integrals, log, integrate", "plant of the next frame", "wait (4)"]
-QUAD_COV = ["predict, A, S0", "wait (1), (2): weights, S^-1", "gain rows, X, U", "wait (3)", "rank update", "wait (4): pinv ... plant"]
+QUAD_CHAIN = ["hold logic, innovation, kernel weights, b", "wait (1): A, S0", "S, L D L^T, S^-1", "gain rows K, X, U", "wait (2)",
+              "wait (3): Gram matrix", "pseudo-inverse", "command, finiteness, publish", "wait (4)", "log, integrals, integrate; plant of the next frame"]
+QUAD_COV = ["predict, A, S0", "wait (1) + noise batch (every 4th frame)", "wait (2): S^-1, gain rows", "Gram + wait (3)", "rank update", "wait (4): pinv"]
 
 
 def main():

@@ -39,6 +39,15 @@
 #define UVS_QUAD_MAXNREG 128
 #endif
 #define UVS_QUAD_BOUNDS __maxnreg__(UVS_QUAD_MAXNREG)
+#ifndef UVS_QUAD_GAIN_UNROLL
+#define UVS_QUAD_GAIN_UNROLL 2
+#endif
+#ifndef UVS_QUAD_GAIN_RB
+#define UVS_QUAD_GAIN_RB 3
+#endif
+#ifndef UVS_QUAD_RANK_UNROLL
+#define UVS_QUAD_RANK_UNROLL 2
+#endif
 
 // profiling build (-DUVS_PHASE_CLOCKS, tools/phase_clocks.py --quad): wall cycles per role and phase, slots 12.. of the buffer
 #ifdef UVS_PHASE_CLOCKS
@@ -54,12 +63,14 @@
 namespace uvs {
 
 constexpr int kQuadFilters = 4;
+constexpr int kQuadGainUnroll = UVS_QUAD_GAIN_UNROLL, kQuadRankUnroll = UVS_QUAD_RANK_UNROLL;
 constexpr int kQuadThreads = (kQuadFilters + 1) * 32;
 
 struct alignas(16) QuadCtl {           // per filter
-    double gain_scale;                 // IMCC-KF: c (1 otherwise)
+    double noise[32];                  // fresh draws of the next 32 / M frames: [slot * M + coordinate]
     int ok;                            // S factorised (else: NOT_SPD, the correction is skipped)
     int alive;                         // the trial is still running
+    int done;                          // the frame before barrier (4) completed (trace rows are written for it)
 };
 
 // the CTA's dynamic shared memory as seen by either role (declared inside each function so that every access is an LDS /
@@ -89,44 +100,149 @@ __host__ __device__ constexpr size_t quad_smem_bytes(int T) {
     return sigma_table_bytes(T) + kQuadFilters * (sizeof(DenseWS<M, false>) + sizeof(QuadCtl)) + 16;
 }
 
-// Gain rows of one filter by its covariance warp: K = gain_scale A S^-1, X += K nu, U = A + (A S^-1) diag(ddiag) (use_D).
-// S^-1 is the explicit symmetric inverse the chain warp left in w.S (the reference also forms it: K = P H^T inv(S),
-// experiment.py:192, 286-287): a row of K is then eight independent 8-term dot products instead of two dependent
-// substitutions, and with the j loop ROLLED the phase needs 16 + ~12 registers next to the warp's 72 of P — unrolled
-// substitutions let ptxas hoist the factor's loads and push half of P into local memory (seen in the SASS).
-template <int M>
-UVS_DEV void quad_gain_rows(DenseWS<M, false>& w, double gain_scale, bool use_D, int lane) {
+// Gain rows by the CHAIN warp: lane gl of group g computes rows gl, gl + 8, ..., of filter g's K = gain_scale A S^-1,
+// RB rows at a time (independent accumulator sets: the chain warp holds no P, it has the registers), then X += K nu and
+// U = A + (A S^-1) diag(ddiag).  The covariance warps do not take part: with P in their registers ptxas serialises this
+// phase on four temporaries (LDS -> DFMA -> LDS on the same registers, measured 6 900 cycles per frame for ~1 000 of work).
+template <int M, int RB>
+UVS_DEV void quad_gain_rows_chain(DenseWS<M, false>& w, double gain_scale, bool use_D, int gl) {
     constexpr int N = 6 * M, LD = N + 2;
-    const double* ddiag = w.ib + 8;
+    const double* __restrict__ At = w.At;
+    const double* __restrict__ Si = w.S;
+    const double* __restrict__ nu = w.nu;
+    const double* __restrict__ ddiag = w.ib + 8;
+    double* __restrict__ Kt = w.Kt;
+    double* __restrict__ Ut = w.Ut;
+    double* __restrict__ X = w.X;
 #pragma unroll 1
-    for (int row = lane; row < N; row += 32) {
-        double kx[M];
+    for (int r0 = gl; r0 < N; r0 += 8 * RB) {
+        int rowv[RB];                                            // rows of this batch (clamped; rows >= N are not stored)
 #pragma unroll
-        for (int k = 0; k < M; ++k) kx[k] = 0.0;
-#pragma unroll 1
+        for (int t = 0; t < RB; ++t) rowv[t] = (r0 + 8 * t < N) ? r0 + 8 * t : r0;
+        double kx[RB][M];
+#pragma unroll
+        for (int t = 0; t < RB; ++t)
+#pragma unroll
+            for (int k = 0; k < M; ++k) kx[t][k] = 0.0;
+#pragma unroll
         for (int j = 0; j < M; ++j) {
-            const double aj = w.At[j * LD + row];
-            const double2* sr = reinterpret_cast<const double2*>(w.S + j * M);      // row j of S^-1 (broadcast)
+            double aj[RB];
+#pragma unroll
+            for (int t = 0; t < RB; ++t) aj[t] = At[j * LD + rowv[t]];
+            const double2* sr = reinterpret_cast<const double2*>(Si + j * M);      // row j of S^-1
 #pragma unroll
             for (int k = 0; k < M; k += 2) {
-                const double2 t = sr[k / 2];
-                kx[k] += aj * t.x;
-                kx[k + 1] += aj * t.y;
+                const double2 s2 = sr[k / 2];
+#pragma unroll
+                for (int t = 0; t < RB; ++t) { kx[t][k] += aj[t] * s2.x; kx[t][k + 1] += aj[t] * s2.y; }
             }
         }
-        double dxr = 0.0;
 #pragma unroll
-        for (int k = 0; k < M; ++k) {
-            w.Kt[k * LD + row] = gain_scale * kx[k];
-            dxr += kx[k] * w.nu[k];
-        }
-        w.X[row] += gain_scale * dxr;                            // experiment.py:193 / 265 / 291
-        if (use_D) {
+        for (int t = 0; t < RB; ++t) {
+            const int row = r0 + 8 * t;
+            if (row < N) {
+                double dxr = 0.0;
 #pragma unroll
-            for (int k = 0; k < M; ++k) w.Ut[k * LD + row] = w.At[k * LD + row] + kx[k] * ddiag[k];
+                for (int k = 0; k < M; ++k) {
+                    Kt[k * LD + row] = gain_scale * kx[t][k];
+                    dxr += kx[t][k] * nu[k];
+                }
+                X[row] += gain_scale * dxr;                      // experiment.py:193 / 265 / 291
+                if (use_D) {
+#pragma unroll
+                    for (int k = 0; k < M; ++k) Ut[k * LD + row] = At[k * LD + row] + kx[t][k] * ddiag[k];
+                }
+            }
         }
     }
+}
+
+// Gram matrix J^T J (21 packed entries) and J^T b (6) of the IBVS normal equations, one entry per lane of the covariance
+// warp (stage 1 of ibvs_with_rank_update, dense.cuh): sc[e] = sum_r J[r][i] q[r].  b was left in sc[27..27+M) by the chain
+// warp before barrier (1).
+template <int M>
+UVS_DEV void quad_gram(const double* __restrict__ J, double* __restrict__ sc, int lane) {
+    const double* sb = sc + 27;
+    const int e = lane < 27 ? lane : 26;
+    const bool gram = e < 21;
+    const int i = gram ? (int)((0x5b6db2491b6d2448ull >> (3 * e)) & 7ull) : e - 21;
+    const int j = e - i * (i + 1) / 2;
+    const double* q = gram ? J + j : sb;         // second factor: column j of J (stride 6) or b (stride 1)
+    const int qs = gram ? 6 : 1;
+    double s = 0.0;
+#pragma unroll
+    for (int r = 0; r < M; ++r) s += J[r * 6 + i] * q[r * qs];
+    if (lane < 27) sc[e] = s;                    // sG = sc[0..21), sg = sc[21..27)
+}
+
+// The rest of the pseudo-inverse by the chain warp's 8-lane groups: pinv_group<M, 8> (smallmat.cuh) from the point where
+// the Gram matrix and J^T b are in sc.  x = pinv(J) b on every lane of the group.
+template <int M>
+UVS_DEV void quad_pinv_from_gram(const double* J, double b_lane, double* sc, int gl, double (&x)[6], int& flags, double* big) {
+    constexpr int K = 6;
+    double* sG = sc;          // 21
+    double* sg = sc + 21;     // 6
+    double* sb = sc + 27;     // 8
+    double* sr = sc + 35;     // 8
+    double* sx = sc + 43;     // 6
+    double L[K * (K + 1) / 2], g[K];
+#pragma unroll
+    for (int i = 0; i < K * (K + 1) / 2; ++i) L[i] = sG[i];
+#pragma unroll
+    for (int i = 0; i < K; ++i) g[i] = sg[i];
+    double gmax = 0.0;
+#pragma unroll
+    for (int i = 0; i < K; ++i) gmax += L[tri(i, i)];
+    bool ok = ldl_packed<K>(L);
+#pragma unroll
+    for (int j = 0; j < K; ++j) ok = ok && (L[tri(j, j)] * gmax * kPinvPivotTol < 1.0);        // L[j][j] = 1 / pivot
+    ldl_solve<K>(L, g);
+    if (gl < M) {
+        double s = b_lane;
+#pragma unroll
+        for (int c = 0; c < 6; ++c) s -= J[gl * 6 + c] * g[c];
+        sr[gl] = s;
+    }
     __syncwarp();
+    if (gl < 6) {
+        double s = 0.0;
+#pragma unroll
+        for (int r = 0; r < M; ++r) s += J[r * 6 + gl] * sr[r];
+        sx[gl] = s;
+    }
+    __syncwarp();
+    double d[K];
+#pragma unroll
+    for (int i = 0; i < K; ++i) d[i] = sx[i];
+    ldl_solve<K>(L, d);
+    double dn2 = 0.0, xn2 = 0.0;
+#pragma unroll
+    for (int i = 0; i < 6; ++i) { x[i] = g[i] + d[i]; dn2 += d[i] * d[i]; xn2 += x[i] * x[i]; }
+    ok = ok && (dn2 <= kPinvRefineTol2 * xn2);
+    __syncwarp();
+    if (!ok) {
+        flags |= UVS_FLAG_RANK_DEFICIENT;
+        int mm = M;
+        asm volatile("" : "+r"(mm));       // see pinv_group
+        pinv_fallback_osj<8>(mm, J, sb, big, sx, gl);
+    }
+    __syncwarp();
+    if (!ok) {
+#pragma unroll
+        for (int i = 0; i < 6; ++i) x[i] = sx[i];
+    }
+    __syncwarp();
+}
+
+// Fresh draws of frames k0 .. k0 + 32/M - 1 of one filter, one per lane of its covariance warp (lane = slot * M +
+// coordinate).  NOT inlined: the samplers (log / tan / pow slow paths) want ~100 registers; as a call the warp saves what
+// it must of P around ONE call site that runs every 32 / M frames, in the shadow of the chain warp's pseudo-inverse.
+template <int M>
+static __device__ __noinline__ void quad_noise_batch(const uvs_noise_params& np, double rho, double alpha, uint64_t trial,
+                                                     int k0, int T, double* out, int lane) {
+    constexpr int FB = 32 / M;
+    const int fs = lane / M;
+    if (fs < FB && k0 + fs < T) out[lane] = noise_sample(np, rho, alpha, trial, (uint32_t)(k0 + fs), (uint32_t)(lane % M));
 }
 
 // P -= K U^T on the lower blocks by the covariance warp: rank_update() of dense.cuh with the k loop of the off-diagonal
@@ -136,9 +252,9 @@ UVS_DEV void quad_gain_rows(DenseWS<M, false>& w, double gain_scale, bool use_D,
 template <int M>
 UVS_DEV void quad_rank_update(PBlock& pb, double* Pd, const double* Kt, const double* Ut, int lane) {
     constexpr int N = 6 * M, LD = N + 2;
-    const double* kp = Kt + 6 * pb.bi;
-    const double* up = Ut + 6 * pb.bj;
-#pragma unroll 1
+    const double* __restrict__ kp = Kt + 6 * pb.bi;
+    const double* __restrict__ up = Ut + 6 * pb.bj;
+#pragma unroll kQuadRankUnroll
     for (int k = 0; k < M; ++k) {
         double ki[6], uj[6];
         load6(kp + k * LD, ki);
@@ -166,18 +282,27 @@ static __device__ __noinline__ void quad_covariance_role(const ClosedLoopArgs& a
     const bool philox = (a.io.noise_in == nullptr) && (cfg.noise.type != UVS_NOISE_NONE);
     const bool traced = io_traced(a.io);
     constexpr bool use_D = METHOD != UVS_METHOD_KF;          // Joseph with R_hat != R (GMCKF) / c != 1 (IMCC-KF)
+    constexpr int FB = 32 / M;                               // frames of noise drawn at once by a covariance warp
     // =================================================================== covariance warp of filter `warp`
     WS& w = wsv[warp];
     QuadCtl& ctl = ctlv[warp];
     volatile int* v_alive = &ctl.alive;
     volatile int* v_ok = &ctl.ok;
+    volatile int* v_done = &ctl.done;
     for (long long b0 = (long long)blockIdx.x * kQuadFilters; b0 < a.B; b0 += (long long)gridDim.x * kQuadFilters) {
         const long long b = b0 + warp;
         const bool trial_ok = b < a.B;
         const long long bb = trial_ok ? b : 0;
         const uint64_t trial = a.trial0 + (uint64_t)bb * a.stride;
+        double rho = cfg.noise.rho, alpha = cfg.noise.alpha;             // noise level of this trial (main.py:121-127)
+        if (cfg.sweep_len > 0 && cfg.sweep_param != 0) {
+            long long lvl = (long long)(trial / (uint64_t)(cfg.sweep_epoch > 0 ? cfg.sweep_epoch : 1));
+            if (lvl >= cfg.sweep_len) lvl = cfg.sweep_len - 1;
+            if (cfg.sweep_param == 1) rho = cfg.sweep[lvl]; else alpha = cfg.sweep[lvl];
+        }
         if (a.io.X0_in)
             for (int r = lane; r < N; r += 32) w.X[r] = a.io.X0_in[bb * N + r];
+        if (philox) quad_noise_batch<M>(cfg.noise, rho, alpha, trial, 0, T, ctl.noise, lane);
         PBlock pb;
         load_P<M>(pb, w.Pd, cfg.P0, UVS_P_DENSE, lane);
         quad_bar();                                                      // init: X, dq, alive, noise published
@@ -188,10 +313,13 @@ static __device__ __noinline__ void quad_covariance_role(const ClosedLoopArgs& a
             // registers while it parks half of P in local memory (seen in the SASS)
             int ln = lane;
             asm volatile("" : "+r"(pb.bi), "+r"(pb.bj), "+r"(ln));
-            const bool live = *v_alive != 0;
+            bool live = *v_alive != 0;
             if (live) {
                 double h[6];                                             // experiment.py:183-188: the previous command
                 load6(w.dq, h);
+                // diagonal of P before P += Q: restored if the chain warp finds the trial ended (feature out of view)
+                // before this frame — it evaluates the plant while this warp predicts
+                for (int row = ln; row < N; row += 32) w.D[row] = w.Pd[(row / 6) * kBlkStride + (row % 6) * 7];
                 predict_and_A<M>(pb, w.Pd, w.At, h, nullptr, 1, ln);
                 __syncwarp();
                 for (int e = ln; e < M * M; e += 32) {                 // S0 = H A (build_and_factor_S)
@@ -206,12 +334,19 @@ static __device__ __noinline__ void quad_covariance_role(const ClosedLoopArgs& a
             }
             QCLK(0);
             quad_bar();                                                  // (1)
-            quad_bar();                                                  // (2) factor published
+            if (live && *v_alive == 0) {                                 // ended out of view: undo the predict
+                for (int row = ln; row < N; row += 32) w.Pd[(row / 6) * kBlkStride + (row % 6) * 7] = w.D[row];
+                live = false;
+            }
+            // while the chain warp factorises S and forms the gain rows: the draws of the next FB frames (the chain warp
+            // read the last of the previous batch before barrier (1) of this frame)
+            if (philox && (k + 1) % FB == 0 && k + 1 < T) quad_noise_batch<M>(cfg.noise, rho, alpha, trial, k + 1, T, ctl.noise, ln);
             QCLK(1);
-            const bool ok = live && (*v_ok != 0);
-            if (ok) quad_gain_rows<M>(w, ctl.gain_scale, use_D, ln);
+            quad_bar();                                                  // (2) K, X, U published
             QCLK(2);
-            quad_bar();                                                  // (3) X published
+            const bool ok = live && (*v_ok != 0);
+            quad_gram<M>(w.X, w.ib, ln);                                 // J = X: Gram matrix and J^T b for the chain warp
+            quad_bar();                                                  // (3)
             QCLK(3);
             if (ok) {
                 quad_rank_update<M>(pb, w.Pd, w.Kt, use_D ? w.Ut : w.At, ln);
@@ -220,7 +355,7 @@ static __device__ __noinline__ void quad_covariance_role(const ClosedLoopArgs& a
             QCLK(4);
             quad_bar();                                                  // (4) dq, alive published
             QCLK(5);
-            if (traced && live && (*v_alive != 0) && trial_ok) {         // state / covariance after the update of frame k
+            if (traced && live && (*v_done != 0) && trial_ok) {          // state / covariance after the update of frame k
                 const size_t bt = (size_t)b * T + k;
                 if (a.io.X_log) for (int r = ln; r < N; r += 32) a.io.X_log[bt * N + r] = w.X[r];
                 if (a.io.P_log)
@@ -253,6 +388,7 @@ static __device__ __noinline__ void quad_chain_role(const ClosedLoopArgs& a) {
     const bool philox = (a.io.noise_in == nullptr) && (cfg.noise.type != UVS_NOISE_NONE);
     const bool traced = io_traced(a.io);
     constexpr bool use_D = METHOD != UVS_METHOD_KF;          // Joseph with R_hat != R (GMCKF) / c != 1 (IMCC-KF)
+    constexpr int FB = 32 / M;                               // frames of noise drawn at once by a covariance warp
     constexpr int LOGW = 6 + 2 * M;
     // =================================================================== chain warp: group g = filter g, lane gl = row
     const int gl = lane & 7, g = lane >> 3;
@@ -267,12 +403,6 @@ static __device__ __noinline__ void quad_chain_role(const ClosedLoopArgs& a) {
         const bool trial_ok = b < a.B;
         const long long bb = trial_ok ? b : 0;
         const uint64_t trial = a.trial0 + (uint64_t)bb * a.stride;
-        double rho = cfg.noise.rho, alpha = cfg.noise.alpha;             // noise level of this trial (main.py:121-127)
-        if (cfg.sweep_len > 0 && cfg.sweep_param != 0) {
-            long long lvl = (long long)(trial / (uint64_t)(cfg.sweep_epoch > 0 ? cfg.sweep_epoch : 1));
-            if (lvl >= cfg.sweep_len) lvl = cfg.sweep_len - 1;
-            if (cfg.sweep_param == 1) rho = cfg.sweep[lvl]; else alpha = cfg.sweep[lvl];
-        }
         double f_l = 0.0, q_l = 0.0;
         {
             double q[6];
@@ -356,8 +486,6 @@ static __device__ __noinline__ void quad_chain_role(const ClosedLoopArgs& a) {
         };
         plant();
         publish_alive();
-        // this lane's fresh draw of frame 0 (counter-based streams: a pure function of (trial, frame, coordinate))
-        double fresh = (philox && rowl) ? noise_sample(cfg.noise, rho, alpha, trial, 0u, (uint32_t)gl) : 0.0;
         quad_bar();                                                      // init
         QCLK_DECL(10)
 
@@ -366,6 +494,7 @@ static __device__ __noinline__ void quad_chain_role(const ClosedLoopArgs& a) {
             double nz = 0.0;
             if (a.io.noise_in) nz = (rowl && trial_ok) ? a.io.noise_in[((size_t)b * T + k) * M + gl] : 0.0;
             else if (philox) {
+                const double fresh = rowl ? ctl.noise[(k % FB) * M + gl] : 0.0;      // drawn by the covariance warp
                 nz = next_noise_prefetched(hs, cfg.noise.hold_cnt, fresh, gl, M);
             }
             const double f_new = f_true + nz;                            // experiment.py:130-135
@@ -390,7 +519,6 @@ static __device__ __noinline__ void quad_chain_role(const ClosedLoopArgs& a) {
                 kappa = c;
                 w_lane = fast_div(1.0, c + 1e-6);
                 if (rowl) w.ib[8 + gl] = w_lane - 1.0;                   // D = R_hat - R (diagonal)
-                if (gl == 0) ctl.gain_scale = 1.0;
             } else if (METHOD == UVS_METHOD_IMCCKF) {                    // experiment.py:258-261
                 double qq = 0.0;
 #pragma unroll
@@ -398,10 +526,10 @@ static __device__ __noinline__ void quad_chain_role(const ClosedLoopArgs& a) {
                 const double c = gaussian_kernel(sqrt(qq), sigma);
                 s0_scale = c;
                 if (rowl) w.ib[8 + gl] = 1.0 - c;                        // D = (1 - c) R
-                if (gl == 0) ctl.gain_scale = c;
-            } else {
-                if (gl == 0) ctl.gain_scale = 1.0;
             }
+            // right-hand side of the IBVS law (experiment.py:306-310), for the covariance warp's J^T b
+            const double b_l = kappa * (f_l - desired);
+            if (rowl) w.ib[27 + gl] = b_l;
             QCLK(0);
             quad_bar();                                                  // (1) A, S0 ready
             QCLK(1);
@@ -428,18 +556,18 @@ static __device__ __noinline__ void quad_chain_role(const ClosedLoopArgs& a) {
                 }
                 if (gl == 0) ctl.ok = ok ? 1 : 0;
             }
+            __syncwarp();                                                // S^-1 complete
             QCLK(2);
-            quad_bar();                                                  // (2)
+            if (ok && alive) quad_gain_rows_chain<M, UVS_QUAD_GAIN_RB>(w, (METHOD == UVS_METHOD_IMCCKF) ? s0_scale : 1.0, use_D, gl);
             QCLK(3);
-            // while the covariance warps solve for the gain rows: the fresh draw of the NEXT frame
-            if (philox && rowl && k + 1 < T) fresh = noise_sample(cfg.noise, rho, alpha, trial, (uint32_t)(k + 1), (uint32_t)gl);
+            quad_bar();                                                  // (2) K, X, U published
             QCLK(4);
-            quad_bar();                                                  // (3) X published
+            quad_bar();                                                  // (3) Gram matrix, J^T b published
             QCLK(5);
             // ---- IBVS: dq = -gain pinv(J) (kappa o error)                  experiment.py:300-312
             double x[6];
             int ib_flags = 0;
-            pinv_group<M, 8>(w.X, kappa * (f_l - desired), w.ib, gl, x, ib_flags, w.jacobi_scratch());
+            quad_pinv_from_gram<M>(w.X, b_l, w.ib, gl, x, ib_flags, w.jacobi_scratch());
             QCLK(6);
             double dq_l = 0.0;
 #pragma unroll
@@ -451,9 +579,22 @@ static __device__ __noinline__ void quad_chain_role(const ClosedLoopArgs& a) {
                 flags_all |= fr_flags;
                 if (bad) { alive = false; status = UVS_STATUS_FAIL; flags_all |= UVS_FLAG_NONFINITE; }
             }
-            if (alive) {
+            const bool done = alive;                                     // frame k completed
+            const size_t bt = (size_t)b * T + k;
+            double dq_cmd = dq_l;                                        // the command the plant executes
+            if (done && gl < 6) {
+                if (a.io.dq_in) dq_cmd = a.io.dq_in[bt * 6 + gl];        // replay gate: recorded command
+                w.dq[gl] = dq_cmd;                                       // experiment.py:183-188: next frame's regressor
+            }
+            publish_alive();
+            if (gl == 0) ctl.done = done ? 1 : 0;
+            QCLK(7);
+            // (4): the command is out — the covariance warps start the next frame's predict while this warp logs,
+            // integrates and evaluates the next frame's plant
+            quad_bar();
+            QCLK(8);
+            if (done) {
                 // logging (experiment.py:323-331) and error integrals (plot_errorbar.m:39-84)
-                const size_t bt = (size_t)b * T + k;
                 if (a.io.log) {
                     double* lg = a.io.log + bt * LOGW;
                     if (gl < 6) lg[gl] = q_l;
@@ -470,22 +611,20 @@ static __device__ __noinline__ void quad_chain_role(const ClosedLoopArgs& a) {
                     if (a.io.kappa_log && rowl) a.io.kappa_log[bt * M + gl] = kappa;
                     if (a.io.flags_log && gl == 0) a.io.flags_log[bt] = fr_flags;
                 }
-                if (a.io.dq_in && gl < 6) dq_l = a.io.dq_in[bt * 6 + gl];                      // replay gate: recorded command
                 if (gl < 6) {                                            // experiment.py:320,335
-                    w.dq[gl] = dq_l;
-                    double v = dq_l;
-                    if (servo) { v = servo_rate(cfg, dq_l, v_prev); v_prev = v; }
+                    double v = dq_cmd;
+                    if (servo) { v = servo_rate(cfg, dq_cmd, v_prev); v_prev = v; }
                     q_l = q_l + v * cfg.dt;
                 }
             }
-            __syncwarp();
-            QCLK(7);
-            if (k + 1 < T) plant();                                      // plant of the next frame
-            publish_alive();
-            QCLK(8);
-            quad_bar();                                                  // (4)
-            QCLK(9);
             if (*quad_alive == 0) break;
+            if (k + 1 < T) {
+                plant();                                                 // plant of the next frame
+                // a feature left the image: the trial ends BEFORE that frame's predict (which the covariance warp has
+                // started meanwhile; it restores P when it sees this after barrier (1))
+                if (gl == 0 && !alive) ctl.alive = 0;
+            }
+            QCLK(9);
         }
         QCLK_FLUSH(10, 12);
         // ||.||_2 over the M coordinates
