@@ -11,9 +11,9 @@ timeout 600 python bench.py --steps 3 --warmup 3 > $O/bench.json 2> $O/bench.err
 cat $O/bench.json
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $O/launches.csv \
     python bench.py --steps 2 --warmup 1 --no-cpu-baseline > $O/bench_under_ncu.log 2>&1
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:dense_closed_loop -c 1 -o $O/dense_full -f \
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:"dense_closed_loop|dense_quad" -c 1 -o $O/dense_full -f \
     python bench.py --steps 1 --warmup 1 --trials 14800 --no-cpu-baseline --no-blockdiag-extra --no-extras > $O/ncu_dense.log 2>&1
-timeout 900 ncu --set full --clock-control none -k regex:dense_closed_loop -c 1 -o $O/dense_full_100k -f \
+timeout 900 ncu --set full --clock-control none -k regex:"dense_closed_loop|dense_quad" -c 1 -o $O/dense_full_100k -f \
     python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-blockdiag-extra --no-extras > $O/ncu_dense_100k.log 2>&1
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:bd_closed_loop -c 1 -o $O/bd_full -f \
     python bench.py --steps 1 --warmup 1 --mode blockdiag --no-cpu-baseline --no-blockdiag-extra --no-extras > $O/ncu_bd.log 2>&1

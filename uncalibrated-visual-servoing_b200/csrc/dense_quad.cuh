@@ -43,7 +43,7 @@
 #define UVS_QUAD_GAIN_UNROLL 2
 #endif
 #ifndef UVS_QUAD_GAIN_RB
-#define UVS_QUAD_GAIN_RB 3
+#define UVS_QUAD_GAIN_RB 2
 #endif
 #ifndef UVS_QUAD_RANK_UNROLL
 #define UVS_QUAD_RANK_UNROLL 2
@@ -77,10 +77,10 @@ struct alignas(16) QuadCtl {           // per filter
 // STS on the shared window, not a generic load through a pointer argument)
 #define QUAD_SMEM_VIEW(MM)                                                                                        \
     extern __shared__ __align__(16) unsigned char smem_raw[];                                                      \
-    DenseWS<MM, false>* wsv = reinterpret_cast<DenseWS<MM, false>*>(smem_raw + sigma_table_bytes(a.cfg.T));        \
-    QuadCtl* ctlv = reinterpret_cast<QuadCtl*>(smem_raw + sigma_table_bytes(a.cfg.T) +                             \
-                                               kQuadFilters * sizeof(DenseWS<MM, false>));                         \
+    unsigned char* ws_base = smem_raw + sigma_table_bytes(a.cfg.T);                                                \
+    QuadCtl* ctlv = reinterpret_cast<QuadCtl*>(ws_base + kQuadFilters * quad_ws_stride<MM>());                     \
     volatile int* quad_alive = reinterpret_cast<volatile int*>(ctlv + kQuadFilters);
+#define QUAD_WS(MM, g) (*reinterpret_cast<DenseWS<MM, false>*>(ws_base + (g) * quad_ws_stride<MM>()))
 
 UVS_DEV void quad_bar() { asm volatile("bar.sync 1, %0;" ::"n"(kQuadThreads) : "memory"); }
 
@@ -95,9 +95,18 @@ UVS_DEV double quad_group_sum(double v) {
     return v;
 }
 
+// Distance between the work spaces of the CTA's four filters: == 64 (mod 128) bytes.  The chain warp's group g reads
+// filter g's arrays with the same offsets in all four groups (8 lanes x 8 B each): with this stride groups 0 / 1 and 2 / 3
+// fall on disjoint halves of the 32 banks and a 64-bit access is its ideal 2 wavefronts (sizeof(DenseWS<8>) == 16 mod
+// 128 put all four groups on overlapping banks: 237 wavefronts per filter-step in the gain phase where 147 are needed, ncu).
+template <int M>
+__host__ __device__ constexpr size_t quad_ws_stride() {
+    return (sizeof(DenseWS<M, false>) + 127) / 128 * 128 + 64;
+}
+
 template <int M>
 __host__ __device__ constexpr size_t quad_smem_bytes(int T) {
-    return sigma_table_bytes(T) + kQuadFilters * (sizeof(DenseWS<M, false>) + sizeof(QuadCtl)) + 16;
+    return sigma_table_bytes(T) + kQuadFilters * (quad_ws_stride<M>() + sizeof(QuadCtl)) + 16;
 }
 
 // Gain rows by the CHAIN warp: lane gl of group g computes rows gl, gl + 8, ..., of filter g's K = gain_scale A S^-1,
@@ -119,41 +128,120 @@ UVS_DEV void quad_gain_rows_chain(DenseWS<M, false>& w, double gain_scale, bool 
         int rowv[RB];                                            // rows of this batch (clamped; rows >= N are not stored)
 #pragma unroll
         for (int t = 0; t < RB; ++t) rowv[t] = (r0 + 8 * t < N) ? r0 + 8 * t : r0;
-        double kx[RB][M];
+        double kx[RB][M], av[RB][M];                             // rows of A are kept for U (no second read)
 #pragma unroll
         for (int t = 0; t < RB; ++t)
 #pragma unroll
-            for (int k = 0; k < M; ++k) kx[t][k] = 0.0;
+            for (int k = 0; k < M; ++k) { kx[t][k] = 0.0; av[t][k] = At[k * LD + rowv[t]]; }
 #pragma unroll
         for (int j = 0; j < M; ++j) {
-            double aj[RB];
-#pragma unroll
-            for (int t = 0; t < RB; ++t) aj[t] = At[j * LD + rowv[t]];
             const double2* sr = reinterpret_cast<const double2*>(Si + j * M);      // row j of S^-1
 #pragma unroll
             for (int k = 0; k < M; k += 2) {
                 const double2 s2 = sr[k / 2];
 #pragma unroll
-                for (int t = 0; t < RB; ++t) { kx[t][k] += aj[t] * s2.x; kx[t][k + 1] += aj[t] * s2.y; }
+                for (int t = 0; t < RB; ++t) { kx[t][k] += av[t][j] * s2.x; kx[t][k + 1] += av[t][j] * s2.y; }
+            }
+        }
+        // epilogue: every load before the first store (the compiler orders shared loads behind earlier shared stores it
+        // cannot prove disjoint: written row by row this was LDS -> DFMA -> STS -> LDS ..., each pair a full shared-memory
+        // round trip, and took half of the chain warp's frame — ncu source view)
+        {
+            double dd[M];
+#pragma unroll
+            for (int k = 0; k < M; ++k) dd[k] = ddiag[k];
+            if (use_D) {
+#pragma unroll
+                for (int t = 0; t < RB; ++t)
+#pragma unroll
+                    for (int k = 0; k < M; ++k) av[t][k] = av[t][k] + kx[t][k] * dd[k];        // row of U
+            }
+        }
+        double dxr[RB], xr[RB];
+        {
+            double nv[M];
+#pragma unroll
+            for (int k = 0; k < M; ++k) nv[k] = nu[k];
+#pragma unroll
+            for (int t = 0; t < RB; ++t) {
+                xr[t] = X[rowv[t]];
+                dxr[t] = 0.0;
+#pragma unroll
+                for (int k = 0; k < M; ++k) dxr[t] += kx[t][k] * nv[k];
             }
         }
 #pragma unroll
         for (int t = 0; t < RB; ++t) {
             const int row = r0 + 8 * t;
             if (row < N) {
-                double dxr = 0.0;
 #pragma unroll
-                for (int k = 0; k < M; ++k) {
-                    Kt[k * LD + row] = gain_scale * kx[t][k];
-                    dxr += kx[t][k] * nu[k];
-                }
-                X[row] += gain_scale * dxr;                      // experiment.py:193 / 265 / 291
+                for (int k = 0; k < M; ++k) Kt[k * LD + row] = gain_scale * kx[t][k];
+                X[row] = xr[t] + gain_scale * dxr[t];            // experiment.py:193 / 265 / 291
                 if (use_D) {
 #pragma unroll
-                    for (int k = 0; k < M; ++k) Ut[k * LD + row] = At[k * LD + row] + kx[t][k] * ddiag[k];
+                    for (int k = 0; k < M; ++k) Ut[k * LD + row] = av[t][k];
                 }
             }
         }
+    }
+}
+
+// P <- P + Q (Q = I), A^T = (P H^T)^T and the lower triangle of S0 = H A by the covariance warp: predict_and_A() of dense.cuh
+// plus build_and_factor_S()'s S0, with S0[bi][bj] = h . (P_bibj h) taken from the registers that hold P_bibj h (the same sum,
+// in the same order, as reading A back from shared memory: 24 wavefronts per filter-step less).  The diagonal of P before
+// the increment is kept in w.D: restored if the chain warp finds that the trial ended (feature out of view) BEFORE this
+// frame — it evaluates the plant while this warp predicts.
+template <int M>
+UVS_DEV void quad_predict(PBlock& pb, DenseWS<M, false>& w, const double (&h)[6], int lane) {
+    constexpr int N = 6 * M, LD = N + 2, NOFF = M * (M - 1) / 2;
+    double* __restrict__ At = w.At;
+    double* __restrict__ S0 = w.S;
+    double* __restrict__ Pd = w.Pd;
+    double* __restrict__ Dsave = w.D;
+    if (lane < NOFF) {
+        const int bi = pb.bi, bj = pb.bj;
+        double lo[6], hi[6];
+#pragma unroll
+        for (int r = 0; r < 6; ++r) {
+            double acc = 0.0;
+#pragma unroll
+            for (int c = 0; c < 6; ++c) acc += pb.v[r][c] * h[c];
+            lo[r] = acc;
+        }
+#pragma unroll
+        for (int c = 0; c < 6; ++c) {
+            double acc = 0.0;
+#pragma unroll
+            for (int r = 0; r < 6; ++r) acc += pb.v[r][c] * h[r];
+            hi[c] = acc;
+        }
+        store6(At + bj * LD + 6 * bi, lo);
+        store6(At + bi * LD + 6 * bj, hi);
+        double s0 = 0.0;
+#pragma unroll
+        for (int r = 0; r < 6; ++r) s0 += h[r] * lo[r];
+        S0[bi * M + bj] = s0;
+    }
+    for (int row = lane; row < N; row += 32) {
+        const int d = row / 6, r = row % 6;
+        double* pr = Pd + d * kBlkStride + r * 6;
+        Dsave[row] = pr[r];
+        pr[r] += 1.0;
+        double v[6];
+        load6(pr, v);
+        double acc = 0.0;
+#pragma unroll
+        for (int c = 0; c < 6; ++c) acc += v[c] * h[c];
+        At[d * LD + row] = acc;
+    }
+    __syncwarp();
+    if (lane < M) {
+        double av[6];
+        load6(At + lane * LD + 6 * lane, av);
+        double s0 = 0.0;
+#pragma unroll
+        for (int r = 0; r < 6; ++r) s0 += h[r] * av[r];
+        S0[lane * M + lane] = s0;
     }
 }
 
@@ -284,7 +372,7 @@ static __device__ __noinline__ void quad_covariance_role(const ClosedLoopArgs& a
     constexpr bool use_D = METHOD != UVS_METHOD_KF;          // Joseph with R_hat != R (GMCKF) / c != 1 (IMCC-KF)
     constexpr int FB = 32 / M;                               // frames of noise drawn at once by a covariance warp
     // =================================================================== covariance warp of filter `warp`
-    WS& w = wsv[warp];
+    WS& w = QUAD_WS(M, warp);
     QuadCtl& ctl = ctlv[warp];
     volatile int* v_alive = &ctl.alive;
     volatile int* v_ok = &ctl.ok;
@@ -317,20 +405,7 @@ static __device__ __noinline__ void quad_covariance_role(const ClosedLoopArgs& a
             if (live) {
                 double h[6];                                             // experiment.py:183-188: the previous command
                 load6(w.dq, h);
-                // diagonal of P before P += Q: restored if the chain warp finds the trial ended (feature out of view)
-                // before this frame — it evaluates the plant while this warp predicts
-                for (int row = ln; row < N; row += 32) w.D[row] = w.Pd[(row / 6) * kBlkStride + (row % 6) * 7];
-                predict_and_A<M>(pb, w.Pd, w.At, h, nullptr, 1, ln);
-                __syncwarp();
-                for (int e = ln; e < M * M; e += 32) {                 // S0 = H A (build_and_factor_S)
-                    const int i = e / M, kk = e % M;
-                    double av[6];
-                    load6(w.At + kk * LD + 6 * i, av);
-                    double s0 = 0.0;
-#pragma unroll
-                    for (int r = 0; r < 6; ++r) s0 += h[r] * av[r];
-                    w.S[e] = s0;
-                }
+                quad_predict<M>(pb, w, h, ln);
             }
             QCLK(0);
             quad_bar();                                                  // (1)
@@ -392,7 +467,7 @@ static __device__ __noinline__ void quad_chain_role(const ClosedLoopArgs& a) {
     constexpr int LOGW = 6 + 2 * M;
     // =================================================================== chain warp: group g = filter g, lane gl = row
     const int gl = lane & 7, g = lane >> 3;
-    WS& w = wsv[g];
+    WS& w = QUAD_WS(M, g);
     QuadCtl& ctl = ctlv[g];
     const bool rowl = gl < M;                                            // this lane carries a measurement row
     const double desired = rowl ? cfg.desired_f[gl] : 0.0;
