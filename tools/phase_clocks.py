@@ -23,9 +23,9 @@ NAMES = ["0 plant: sincos, point in camera, pixel", "1 noise (Philox alpha-stabl
          "11 frame tail: dq, finiteness, integrals, integrate"]
 
 
-QUAD_CHAIN = ["hold logic, innovation, kernel weights, b", "wait (1): A, S0", "S, L D L^T, S^-1", "gain rows K, X, U", "wait (2)",
-              "wait (3): Gram matrix", "pseudo-inverse", "command, finiteness, publish", "wait (4)", "log, integrals, integrate; plant of the next frame"]
-QUAD_COV = ["predict, A, S0", "wait (1) + noise batch (every 4th frame)", "wait (2): S^-1, gain rows", "Gram + wait (3)", "rank update", "wait (4): pinv"]
+QUAD_CHAIN = ["hold logic, innovation, kernel weights, b", "wait (1): A, S0", "S, L D L^T, S^-1, y", "wait (2)", "gain rows K, U",
+              "wait (3): X, Gram matrix", "pseudo-inverse", "command, finiteness, publish", "wait (4)", "log, integrals, integrate; plant of the next frame"]
+QUAD_COV = ["predict, A, S0", "wait (1)", "wait (2): S^-1, y", "X += A y, Gram, noise batch (every 4th frame), wait (3)", "rank update", "wait (4): pinv"]
 
 
 def main():

@@ -67,7 +67,7 @@ constexpr int kQuadGainUnroll = UVS_QUAD_GAIN_UNROLL, kQuadRankUnroll = UVS_QUAD
 constexpr int kQuadThreads = (kQuadFilters + 1) * 32;
 
 struct alignas(16) QuadCtl {           // per filter
-    double noise[32];                  // fresh draws of the next 32 / M frames: [slot * M + coordinate]
+    double noise[2][32];               // fresh draws of 32 / M frames, double-buffered by batch: [batch & 1][slot * M + coordinate]
     int ok;                            // S factorised (else: NOT_SPD, the correction is skipped)
     int alive;                         // the trial is still running
     int done;                          // the frame before barrier (4) completed (trace rows are written for it)
@@ -82,7 +82,15 @@ struct alignas(16) QuadCtl {           // per filter
     volatile int* quad_alive = reinterpret_cast<volatile int*>(ctlv + kQuadFilters);
 #define QUAD_WS(MM, g) (*reinterpret_cast<DenseWS<MM, false>*>(ws_base + (g) * quad_ws_stride<MM>()))
 
-UVS_DEV void quad_bar() { asm volatile("bar.sync 1, %0;" ::"n"(kQuadThreads) : "memory"); }
+// Named barriers of the CTA.  quad_bar(): everybody waits (trial start / end).  The four per-frame barriers (ids 1..4)
+// are split: a role that only PUBLISHES at a barrier arrives without waiting (bar.arrive) and goes on; the role that
+// CONSUMES waits (bar.sync).  Covariance warps: arrive (1), wait (2) (3) (4); chain warp: wait (1) (3), arrive (2) (4).
+UVS_DEV void quad_bar() { asm volatile("bar.sync 5, %0;" ::"n"(kQuadThreads) : "memory"); }
+template <int ID> UVS_DEV void quad_wait() { asm volatile("bar.sync %0, %1;" ::"n"(ID), "n"(kQuadThreads) : "memory"); }
+template <int ID> UVS_DEV void quad_arrive() {
+    __threadfence_block();
+    asm volatile("bar.arrive %0, %1;" ::"n"(ID), "n"(kQuadThreads) : "memory");
+}
 
 UVS_DEV bool quad_group_any(bool p, int lane) {
     const unsigned b = __ballot_sync(UVS_FULL_MASK, p);
@@ -118,11 +126,9 @@ UVS_DEV void quad_gain_rows_chain(DenseWS<M, false>& w, double gain_scale, bool 
     constexpr int N = 6 * M, LD = N + 2;
     const double* __restrict__ At = w.At;
     const double* __restrict__ Si = w.S;
-    const double* __restrict__ nu = w.nu;
-    const double* __restrict__ ddiag = w.ib + 8;
+    const double* __restrict__ ddiag = w.Lc + 8;      // w.Lc: y [0..M), ddiag [8..8+M) (w.ib is the Gram matrix's, written meanwhile)
     double* __restrict__ Kt = w.Kt;
     double* __restrict__ Ut = w.Ut;
-    double* __restrict__ X = w.X;
 #pragma unroll 1
     for (int r0 = gl; r0 < N; r0 += 8 * RB) {
         int rowv[RB];                                            // rows of this batch (clamped; rows >= N are not stored)
@@ -157,26 +163,12 @@ UVS_DEV void quad_gain_rows_chain(DenseWS<M, false>& w, double gain_scale, bool 
                     for (int k = 0; k < M; ++k) av[t][k] = av[t][k] + kx[t][k] * dd[k];        // row of U
             }
         }
-        double dxr[RB], xr[RB];
-        {
-            double nv[M];
-#pragma unroll
-            for (int k = 0; k < M; ++k) nv[k] = nu[k];
-#pragma unroll
-            for (int t = 0; t < RB; ++t) {
-                xr[t] = X[rowv[t]];
-                dxr[t] = 0.0;
-#pragma unroll
-                for (int k = 0; k < M; ++k) dxr[t] += kx[t][k] * nv[k];
-            }
-        }
 #pragma unroll
         for (int t = 0; t < RB; ++t) {
             const int row = r0 + 8 * t;
             if (row < N) {
 #pragma unroll
                 for (int k = 0; k < M; ++k) Kt[k * LD + row] = gain_scale * kx[t][k];
-                X[row] = xr[t] + gain_scale * dxr[t];            // experiment.py:193 / 265 / 291
                 if (use_D) {
 #pragma unroll
                     for (int k = 0; k < M; ++k) Ut[k * LD + row] = av[t][k];
@@ -242,6 +234,31 @@ UVS_DEV void quad_predict(PBlock& pb, DenseWS<M, false>& w, const double (&h)[6]
 #pragma unroll
         for (int r = 0; r < 6; ++r) s0 += h[r] * av[r];
         S0[lane * M + lane] = s0;
+    }
+}
+
+// X += A y by the covariance warp (y in w.Lc[0..M), left there by the chain warp)
+template <int M>
+UVS_DEV void quad_state_update(DenseWS<M, false>& w, int lane) {
+    constexpr int N = 6 * M, LD = N + 2;
+    const double* __restrict__ At = w.At;
+    const double* __restrict__ yv = w.Lc;
+    double* __restrict__ X = w.X;
+    double y[M];
+#pragma unroll
+    for (int j = 0; j < M; j += 2) {
+        const double2 t = *reinterpret_cast<const double2*>(yv + j);
+        y[j] = t.x; y[j + 1] = t.y;
+    }
+    for (int row = lane; row < N; row += 32) {
+        double a[M];
+#pragma unroll
+        for (int j = 0; j < M; ++j) a[j] = At[j * LD + row];
+        const double x0 = X[row];
+        double dx = 0.0;
+#pragma unroll
+        for (int j = 0; j < M; ++j) dx += a[j] * y[j];
+        X[row] = x0 + dx;
     }
 }
 
@@ -390,7 +407,7 @@ static __device__ __noinline__ void quad_covariance_role(const ClosedLoopArgs& a
         }
         if (a.io.X0_in)
             for (int r = lane; r < N; r += 32) w.X[r] = a.io.X0_in[bb * N + r];
-        if (philox) quad_noise_batch<M>(cfg.noise, rho, alpha, trial, 0, T, ctl.noise, lane);
+        if (philox) quad_noise_batch<M>(cfg.noise, rho, alpha, trial, 0, T, ctl.noise[0], lane);
         PBlock pb;
         load_P<M>(pb, w.Pd, cfg.P0, UVS_P_DENSE, lane);
         quad_bar();                                                      // init: X, dq, alive, noise published
@@ -408,27 +425,32 @@ static __device__ __noinline__ void quad_covariance_role(const ClosedLoopArgs& a
                 quad_predict<M>(pb, w, h, ln);
             }
             QCLK(0);
-            quad_bar();                                                  // (1)
+            quad_arrive<1>();                                            // (1) A, S0 published
+            // the draws of the next FB frames, into the other half of the noise buffer, while the chain warp finishes the
+            // measurement and factorises S
+            if (philox && (k + 1) % FB == 0 && k + 1 < T)
+                quad_noise_batch<M>(cfg.noise, rho, alpha, trial, k + 1, T, ctl.noise[((k + 1) / FB) & 1], ln);
+            QCLK(1);
+            quad_wait<2>();                                              // (2) S^-1, y published
+            QCLK(2);
             if (live && *v_alive == 0) {                                 // ended out of view: undo the predict
                 for (int row = ln; row < N; row += 32) w.Pd[(row / 6) * kBlkStride + (row % 6) * 7] = w.D[row];
                 live = false;
             }
-            // while the chain warp factorises S and forms the gain rows: the draws of the next FB frames (the chain warp
-            // read the last of the previous batch before barrier (1) of this frame)
-            if (philox && (k + 1) % FB == 0 && k + 1 < T) quad_noise_batch<M>(cfg.noise, rho, alpha, trial, k + 1, T, ctl.noise, ln);
-            QCLK(1);
-            quad_bar();                                                  // (2) K, X, U published
-            QCLK(2);
             const bool ok = live && (*v_ok != 0);
-            quad_gram<M>(w.X, w.ib, ln);                                 // J = X: Gram matrix and J^T b for the chain warp
-            quad_bar();                                                  // (3)
+            // while the chain warp forms the gain rows K = A S^-1 and U: the state correction X += A y, y = gain_scale S^-1 nu
+            // (experiment.py:193 / 265 / 291: X + K nu = X + A (S^-1 nu)), then, with J = X, the Gram matrix and J^T b
+            if (ok) quad_state_update<M>(w, ln);
+            __syncwarp();
+            quad_gram<M>(w.X, w.ib, ln);
+            quad_wait<3>();                                              // (3) X, Gram | K, U
             QCLK(3);
             if (ok) {
                 quad_rank_update<M>(pb, w.Pd, w.Kt, use_D ? w.Ut : w.At, ln);
                 __syncwarp();
             }
             QCLK(4);
-            quad_bar();                                                  // (4) dq, alive published
+            quad_wait<4>();                                              // (4) dq, alive published
             QCLK(5);
             if (traced && live && (*v_done != 0) && trial_ok) {          // state / covariance after the update of frame k
                 const size_t bt = (size_t)b * T + k;
@@ -569,7 +591,7 @@ static __device__ __noinline__ void quad_chain_role(const ClosedLoopArgs& a) {
             double nz = 0.0;
             if (a.io.noise_in) nz = (rowl && trial_ok) ? a.io.noise_in[((size_t)b * T + k) * M + gl] : 0.0;
             else if (philox) {
-                const double fresh = rowl ? ctl.noise[(k % FB) * M + gl] : 0.0;      // drawn by the covariance warp
+                const double fresh = rowl ? ctl.noise[(k / FB) & 1][(k % FB) * M + gl] : 0.0;      // drawn by the covariance warp
                 nz = next_noise_prefetched(hs, cfg.noise.hold_cnt, fresh, gl, M);
             }
             const double f_new = f_true + nz;                            // experiment.py:130-135
@@ -593,20 +615,20 @@ static __device__ __noinline__ void quad_chain_role(const ClosedLoopArgs& a) {
                 const double c = rowl ? exp(-0.5 * (nu_l * nu_l) * inv_s2) : 1.0;
                 kappa = c;
                 w_lane = fast_div(1.0, c + 1e-6);
-                if (rowl) w.ib[8 + gl] = w_lane - 1.0;                   // D = R_hat - R (diagonal)
+                if (rowl) w.Lc[8 + gl] = w_lane - 1.0;                   // D = R_hat - R (diagonal)
             } else if (METHOD == UVS_METHOD_IMCCKF) {                    // experiment.py:258-261
                 double qq = 0.0;
 #pragma unroll
                 for (int j = 0; j < M; ++j) { const double ej = __shfl_sync(UVS_FULL_MASK, nu_l, j, 8); qq += ej * ej; }
                 const double c = gaussian_kernel(sqrt(qq), sigma);
                 s0_scale = c;
-                if (rowl) w.ib[8 + gl] = 1.0 - c;                        // D = (1 - c) R
+                if (rowl) w.Lc[8 + gl] = 1.0 - c;                        // D = (1 - c) R
             }
             // right-hand side of the IBVS law (experiment.py:306-310), for the covariance warp's J^T b
             const double b_l = kappa * (f_l - desired);
             if (rowl) w.ib[27 + gl] = b_l;
             QCLK(0);
-            quad_bar();                                                  // (1) A, S0 ready
+            quad_wait<1>();                                              // (1) A, S0 ready
             QCLK(1);
             // ---- S = s0_scale S0 + R_hat, L D L^T (redundant in the 8 lanes of the group) ---------------
             bool ok;
@@ -628,16 +650,20 @@ static __device__ __noinline__ void quad_chain_role(const ClosedLoopArgs& a) {
                     ldl_solve<M>(L, e);
 #pragma unroll
                     for (int j = 0; j < M; j += 2) *reinterpret_cast<double2*>(w.S + gl * M + j) = make_double2(e[j], e[j + 1]);
+                    // y = gain_scale S^-1 nu: the state correction is X += A y (covariance warp, while this warp forms K)
+                    double y = 0.0;
+#pragma unroll
+                    for (int j = 0; j < M; ++j) y += e[j] * w.nu[j];
+                    w.Lc[gl] = ((METHOD == UVS_METHOD_IMCCKF) ? s0_scale : 1.0) * y;
                 }
                 if (gl == 0) ctl.ok = ok ? 1 : 0;
             }
-            __syncwarp();                                                // S^-1 complete
             QCLK(2);
-            if (ok && alive) quad_gain_rows_chain<M, UVS_QUAD_GAIN_RB>(w, (METHOD == UVS_METHOD_IMCCKF) ? s0_scale : 1.0, use_D, gl);
+            quad_arrive<2>();                                            // (2) S^-1, y published
             QCLK(3);
-            quad_bar();                                                  // (2) K, X, U published
+            if (ok && alive) quad_gain_rows_chain<M, UVS_QUAD_GAIN_RB>(w, (METHOD == UVS_METHOD_IMCCKF) ? s0_scale : 1.0, use_D, gl);
             QCLK(4);
-            quad_bar();                                                  // (3) Gram matrix, J^T b published
+            quad_wait<3>();                                              // (3) K, U | X, Gram matrix, J^T b published
             QCLK(5);
             // ---- IBVS: dq = -gain pinv(J) (kappa o error)                  experiment.py:300-312
             double x[6];
@@ -664,9 +690,10 @@ static __device__ __noinline__ void quad_chain_role(const ClosedLoopArgs& a) {
             publish_alive();
             if (gl == 0) ctl.done = done ? 1 : 0;
             QCLK(7);
-            // (4): the command is out — the covariance warps start the next frame's predict while this warp logs,
-            // integrates and evaluates the next frame's plant
-            quad_bar();
+            // (4): the command is out — the covariance warps start the next frame's predict (when their rank update is
+            // done: this warp does not wait for it) while this warp logs, integrates and evaluates the next frame's plant
+            const bool any_alive = __any_sync(UVS_FULL_MASK, alive);
+            quad_arrive<4>();
             QCLK(8);
             if (done) {
                 // logging (experiment.py:323-331) and error integrals (plot_errorbar.m:39-84)
@@ -692,7 +719,7 @@ static __device__ __noinline__ void quad_chain_role(const ClosedLoopArgs& a) {
                     q_l = q_l + v * cfg.dt;
                 }
             }
-            if (*quad_alive == 0) break;
+            if (!any_alive) break;
             if (k + 1 < T) {
                 plant();                                                 // plant of the next frame
                 // a feature left the image: the trial ends BEFORE that frame's predict (which the covariance warp has
