@@ -398,9 +398,9 @@ def run_ours(a):
             torch.cuda.synchronize()
             pcie = big.numel() * 8 / (l0.elapsed_time(l1) * 1e-3) / 1e9
             del big, host
-            # chunk = 4 whole waves of the dense kernel's persistent grid (148 SMs x 2 CTAs x 4 filters = 1184 per wave):
-            # a chunk that ends mid-wave leaves SMs idle at every chunk boundary (measured: 4096 -> 0.84 of the rate)
-            CH = 4 * 1184
+            # chunk = 3 whole waves of the dense kernel's persistent grid (quad kernel: 148 SMs x 3 CTAs x 4 filters = 1776
+            # per wave): a chunk that ends mid-wave leaves SMs idle at every chunk boundary (measured: 4096 -> 0.84 of the rate)
+            CH = 3 * 1776
             E.closed_loop_stream(cfgl, trial0, 2 * CH, chunk=CH)                    # warm-up (allocations, page locking)
             Bs = min(B, 8 * CH)
             si = E.closed_loop_stream(cfgl, trial0, Bs, chunk=CH)
@@ -452,6 +452,10 @@ def run_ours(a):
         return
     steps_per_launch = main["local_frames"]
     achieved = steps_per_launch * F_ALG / (main["kernel_ms"] * 1e-3) / 1e12
+    # the dense family's FAST configuration (Q = R = NULL, Joseph) runs the warp-specialised quad kernel (csrc/dense_quad.cuh)
+    # unless UVS_DENSE_QUAD=0 asks for the one-filter-per-warp kernel (comparison runs)
+    quad = a.mode == "dense" and os.environ.get("UVS_DENSE_QUAD", "1")[:1] != "0"
+    kernel_name = "dense_quad_kernel<8, GMCKF>" if quad else f"{a.mode}_closed_loop_kernel<8, GMCKF>"
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
         "ms_per_step": main["ms_total"] / a.steps, "higher_is_better": True, "scaling": scaling, "vs_baseline": None,
@@ -469,9 +473,9 @@ def run_ours(a):
                        "buffers out; launch, D2H of the per-trial results and stream synchronisation inside the timed region)"},
         "gpu_launches": 2 * a.steps,      # per step: the closed-loop kernel + the statistics reduction
         "roofline": {"bound": "fp64", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s",
-                     "frac": achieved / peak_tf, "traffic": ncu_traffic(f"{a.mode}_closed_loop_kernel<8, GMCKF>"),
+                     "frac": achieved / peak_tf, "traffic": ncu_traffic(kernel_name),
                      "traffic_unit": "bytes per launch (ncu dram read + write); algorithmic: 32 B per trial of results",
-                     "kernel": f"{a.mode}_closed_loop_kernel<8, GMCKF>", "kernel_ms": main["kernel_ms"],
+                     "kernel": kernel_name, "kernel_ms": main["kernel_ms"],
                      "flops_per_filter_step_algorithmic": F_ALG,
                      "flops_per_filter_step_executed": ncu_traffic("dense_executed_flops_per_filter_step") if a.mode == "dense" else None,
                      "peak_source": "measured in this run: uvs_fp64_peak (register-resident DFMA chains on every SM); "

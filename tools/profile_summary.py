@@ -95,8 +95,8 @@ def main():
                     pass
             ir, iw = hdr.index("dram__bytes_read.sum"), hdr.index("dram__bytes_write.sum")
             if rep not in ("dense_full", "twist_full"):            # bench-sized launches only
-                key = ("dense" if "dense" in name else "bd") + "_closed_loop_kernel<8, GMCKF>"
-                key = key.replace("bd_", "blockdiag_")
+                key = "dense_quad_kernel<8, GMCKF>" if "dense_quad" in name else \
+                    ("dense" if "dense" in name else "blockdiag") + "_closed_loop_kernel<8, GMCKF>"
                 traffic[key] = to_bytes(v[ir], units[ir]) + to_bytes(v[iw], units[iw])
     with open(os.path.join(dst, f"{label}_ncu_full_summary.md"), "w") as fh:
         fh.write("\n".join(md) + "\n")
@@ -111,6 +111,11 @@ def main():
         sass = os.path.join("/tmp", f"{label}_sass.csv")
         with open(sass, "w") as fh:
             subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], stdout=fh, stderr=subprocess.DEVNULL)
+        # per-phase view of the quad kernel (regions between its named barriers = the hand-over points of the two roles)
+        out = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "ncu_regions.py"), sass, str(14800 * 300)],
+                             capture_output=True, text=True).stdout
+        with open(os.path.join(dst, f"{label}_dense_by_region.txt"), "w") as fh:
+            fh.write(out)
         cub = "/tmp/uvs_cubin"
         os.makedirs(cub, exist_ok=True)
         subprocess.run(["cuobjdump", "-xelf", "dense_m8", os.path.join(ROOT, "uncalibrated-visual-servoing_b200", "libuvs_b200.so")],
@@ -118,7 +123,7 @@ def main():
         cubin = [f for f in os.listdir(cub) if f.startswith("dense_m8")]
         if cubin:
             out = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "ncu_by_line.py"), sass,
-                                  os.path.join(cub, cubin[0]), "dense_closed_loop_kernelILi8ELi5ELb1", "40"],
+                                  os.path.join(cub, cubin[0]), "dense_quad_kernelILi8ELi5", "40"],
                                  capture_output=True, text=True).stdout
             with open(os.path.join(dst, f"{label}_dense_by_line.txt"), "w") as fh:
                 fh.write(out)

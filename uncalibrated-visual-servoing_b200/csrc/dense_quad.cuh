@@ -85,11 +85,20 @@ struct alignas(16) QuadCtl {           // per filter
 // Named barriers of the CTA.  quad_bar(): everybody waits (trial start / end).  The four per-frame barriers (ids 1..4)
 // are split: a role that only PUBLISHES at a barrier arrives without waiting (bar.arrive) and goes on; the role that
 // CONSUMES waits (bar.sync).  Covariance warps: arrive (1), wait (2) (3) (4); chain warp: wait (1) (3), arrive (2) (4).
-UVS_DEV void quad_bar() { asm volatile("bar.sync 5, %0;" ::"n"(kQuadThreads) : "memory"); }
-template <int ID> UVS_DEV void quad_wait() { asm volatile("bar.sync %0, %1;" ::"n"(ID), "n"(kQuadThreads) : "memory"); }
+// The warp reconverges (__syncwarp) before it touches a CTA barrier, and the barrier instructions are the non-.aligned
+// forms: after lane-dependent loops the lanes of a warp are not guaranteed to arrive together (compute-sanitizer synccheck).
+UVS_DEV void quad_bar() {
+    __syncwarp();
+    asm volatile("barrier.sync 5, %0;" ::"n"(kQuadThreads) : "memory");
+}
+template <int ID> UVS_DEV void quad_wait() {
+    __syncwarp();
+    asm volatile("barrier.sync %0, %1;" ::"n"(ID), "n"(kQuadThreads) : "memory");
+}
 template <int ID> UVS_DEV void quad_arrive() {
+    __syncwarp();
     __threadfence_block();
-    asm volatile("bar.arrive %0, %1;" ::"n"(ID), "n"(kQuadThreads) : "memory");
+    asm volatile("barrier.arrive %0, %1;" ::"n"(ID), "n"(kQuadThreads) : "memory");
 }
 
 UVS_DEV bool quad_group_any(bool p, int lane) {
@@ -659,8 +668,8 @@ static __device__ __noinline__ void quad_chain_role(const ClosedLoopArgs& a) {
                 if (gl == 0) ctl.ok = ok ? 1 : 0;
             }
             QCLK(2);
-            quad_arrive<2>();                                            // (2) S^-1, y published
-            QCLK(3);
+            quad_arrive<2>();                                            // (2) S^-1, y published (the group's S^-1 is complete:
+            QCLK(3);                                                     //     the arrival starts with a __syncwarp)
             if (ok && alive) quad_gain_rows_chain<M, UVS_QUAD_GAIN_RB>(w, (METHOD == UVS_METHOD_IMCCKF) ? s0_scale : 1.0, use_D, gl);
             QCLK(4);
             quad_wait<3>();                                              // (3) K, U | X, Gram matrix, J^T b published
