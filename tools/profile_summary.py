@@ -118,9 +118,9 @@ def main():
             fh.write(out)
         cub = "/tmp/uvs_cubin"
         os.makedirs(cub, exist_ok=True)
-        subprocess.run(["cuobjdump", "-xelf", "dense_m8", os.path.join(ROOT, "uncalibrated-visual-servoing_b200", "libuvs_b200.so")],
+        subprocess.run(["cuobjdump", "-xelf", "dense_quad_m8", os.path.join(ROOT, "uncalibrated-visual-servoing_b200", "libuvs_b200.so")],
                        cwd=cub, capture_output=True)
-        cubin = [f for f in os.listdir(cub) if f.startswith("dense_m8")]
+        cubin = [f for f in os.listdir(cub) if f.startswith("dense_quad_m8")]
         if cubin:
             out = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "ncu_by_line.py"), sass,
                                   os.path.join(cub, cubin[0]), "dense_quad_kernelILi8ELi5", "40"],

@@ -16,8 +16,9 @@ CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(HERE, "build")
 # tuning builds: UVS_DENSE_MINB=<n> python build.py --out libuvs_b200_minb<n>.so ; select with UVS_B200_LIB=<path>
 LIB = os.path.join(HERE, "libuvs_b200.so")
-SOURCES = ["api.cu", "aux_kernels.cu", "blockdiag_kernels.cu", "dense_m2.cu", "dense_m6.cu", "dense_m8.cu",
-           "twist_m2.cu", "twist_m6.cu", "twist_m8.cu"]
+# longest compiles first (8 worker threads): the per-M units of the three kernel families dominate the build
+SOURCES = ["blockdiag_m8.cu", "blockdiag_m6.cu", "twist_m8.cu", "dense_m8.cu", "twist_m6.cu", "dense_m6.cu", "blockdiag_m2.cu",
+           "dense_m2.cu", "twist_m2.cu", "dense_quad_m8.cu", "dense_quad_m6.cu", "api.cu", "aux_kernels.cu", "blockdiag_kernels.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
          "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", "--expt-relaxed-constexpr",

@@ -362,8 +362,12 @@ __global__ void UVS_DENSE_BOUNDS dense_closed_loop_kernel(const __grid_constant_
     }
 }
 
-template <int M, int METHOD>
-static bool quad_try(const ClosedLoopArgs& a, int sms, cudaStream_t st, cudaError_t* err);      // dense_quad.cuh
+// FAST closed-loop launch of the dense family through the warp-specialised quad kernel (dense_quad.cuh; its kernels are
+// compiled in their own translation units dense_quad_m{6,8}.cu): true (and *err set) when it took the launch.
+template <int M> bool launch_dense_quad(const ClosedLoopArgs& a, int sms, cudaStream_t st, cudaError_t* err);
+template <> inline bool launch_dense_quad<2>(const ClosedLoopArgs&, int, cudaStream_t, cudaError_t*) { return false; }
+template <> bool launch_dense_quad<6>(const ClosedLoopArgs& a, int sms, cudaStream_t st, cudaError_t* err);
+template <> bool launch_dense_quad<8>(const ClosedLoopArgs& a, int sms, cudaStream_t st, cudaError_t* err);
 
 // host-side dispatch (defined once per M in dense_m*.cu): persistent grid = SMs x resident CTAs
 template <int M> cudaError_t launch_dense_replay(const ReplayArgs& a, int sms, cudaStream_t st);
@@ -397,7 +401,7 @@ static cudaError_t dense_launch(Kernel kernel, const Args& a, long long B, size_
         const uvs_filter_params& fp = a.cfg.filt;                                                            \
         if (UVS_DENSE_FAST && fp.Q == nullptr && fp.R == nullptr && fp.joseph && !scene_plant(a.cfg)) {      \
             cudaError_t qe;                                                                                  \
-            if (quad_try<MM, METHOD>(a, sms, st, &qe)) return qe;      /* dense_quad.cuh: four filters per CTA */ \
+            if (METHOD != UVS_METHOD_MCKF && launch_dense_quad<MM>(a, sms, st, &qe)) return qe;   /* four filters per CTA */ \
             return dense_launch(dense_closed_loop_kernel<MM, METHOD, UVS_DENSE_FAST != 0>, a, a.B,           \
                                 dense_smem_bytes<MM, METHOD == UVS_METHOD_MCKF>(kDenseWarps) +               \
                                     sigma_table_bytes(a.cfg.T), sms, st);                                    \

@@ -1,5 +1,5 @@
 // dense_m6.cu — instantiates the dense (general covariance) kernels for M = 6 measurements.
-#include "dense_quad.cuh"
+#include "dense_kernels.cuh"
 namespace uvs {
 UVS_DEFINE_DENSE_LAUNCHERS(6)
 }

@@ -808,16 +808,16 @@ static inline bool quad_enabled() {
     return !(e && e[0] == '0');
 }
 
-// FAST closed-loop launch of the dense family: true (and *err set) when the quad kernel took it
-template <int M, int METHOD>
-static bool quad_try(const ClosedLoopArgs& a, int sms, cudaStream_t st, cudaError_t* err) {
-    if constexpr (M >= 6 && METHOD != UVS_METHOD_MCKF) {
-        if (!quad_enabled()) return false;
-        *err = quad_launch<M, METHOD>(a, sms, st);
-        return true;
-    } else {
-        return false;
+// defines launch_dense_quad<MM> (declared in dense_kernels.cuh) in dense_quad_m{6,8}.cu
+#define UVS_DEFINE_QUAD_LAUNCHER(MM)                                                                                  \
+    template <> bool launch_dense_quad<MM>(const ClosedLoopArgs& a, int sms, cudaStream_t st, cudaError_t* err) {      \
+        if (!quad_enabled()) return false;                                                                             \
+        switch (a.cfg.filt.method) {                                                                                   \
+        case UVS_METHOD_KF: *err = quad_launch<MM, UVS_METHOD_KF>(a, sms, st); return true;                            \
+        case UVS_METHOD_IMCCKF: *err = quad_launch<MM, UVS_METHOD_IMCCKF>(a, sms, st); return true;                    \
+        case UVS_METHOD_GMCKF: *err = quad_launch<MM, UVS_METHOD_GMCKF>(a, sms, st); return true;                      \
+        default: return false;                                                                                         \
+        }                                                                                                              \
     }
-}
 
 }  // namespace uvs
