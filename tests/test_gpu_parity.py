@@ -791,3 +791,52 @@ def test_closed_loop_rank_deficient_start_uses_the_fallback(uvs, nf):
         for b in range(B):
             dq0 = (log[b, 1, 0:6] - log[b, 0, 0:6]) / 0.05                 # frame 0: H = 0, the filter leaves X0 untouched
             assert rel_err(dq0, dq_ref) <= 1e-8, (nf, mode, b, dq0, dq_ref)
+
+
+@pytest.mark.parametrize("method", ["KF", "IMCCKF", "GMCKF"])
+@pytest.mark.parametrize("nf", [3, 4])
+def test_quad_kernel_matches_one_filter_per_warp_kernel(uvs, nf, method, monkeypatch):
+    """The dense family's two closed-loop kernels on the SAME inputs (csrc/dense_quad.cuh vs csrc/dense_kernels.cuh; the
+    environment variable UVS_DENSE_QUAD=0 selects the second at launch time).  A free closed-loop run with heavy-tailed noise
+    and the field-of-view check records noise, start poses and commands; both kernels then replay it (noise_in, q0_in, dq_in),
+    so every trial sees the same trajectory and ends — several of them out of view, mid-run — on the same frame: status,
+    frame counts and flags equal, X / P / command / weights of every completed frame and the final X and P (the quad kernel's
+    covariance warp has already started the predict of the frame its chain warp finds out of view, and must undo it)
+    within 1e-9 (the kernels differ in the association of the gain: explicit S^-1 vs two substitutions per row)."""
+    L, E = uvs._lib, uvs.engine
+    m, N = 2 * nf, 12 * nf
+    desired = {3: [153.5, 144.5, 125.5, 116.5, 99.5, 144.5], 4: [149.0, 145.0, 125.0, 121.0, 101.0, 145.0, 125.0, 169.0]}[nf]
+    q0 = [0.0, 0.0, 1.96349541, 0.0, -1.57079633, 0.0]
+    B, T = 37, 60                                        # 37: the last CTA of the quad kernel runs one filter of four
+    # RMCKF with its usual bandwidth shrugs this noise off and loses no trial: a wide kernel makes it as fragile as the KF
+    p = E.filter_params(METHODS[method], nf, mode=L.MODE_DENSE, kernel_bw=1e4 if method == "GMCKF" else 10.0,
+                        annealing=(method == "IMCCKF"))
+    noise = E.noise_params(L.NOISE_ALPHA_STABLE, seed=77 + nf, alpha=1.05, beta=0.0, gamma=3.0, delta=0.0)
+    mk = lambda nz: E.closed_loop_cfg(p, nz, T=T, dt=0.05, ibvs_gain=0.6, q_start=q0, desired_f=desired,      # noqa: E731
+                                      change_q_start=True, pose_seed=5, fov_check=True)
+    monkeypatch.setenv("UVS_DENSE_QUAD", "0")
+    free = E.closed_loop(mk(noise), 0, B, want_log=True, want_trace=True)
+    fr = free["frames"].cpu().numpy()
+    assert ((fr > 0) & (fr < T)).sum() >= 1, fr          # at least one trial ends mid-run (the robust estimators lose few)
+    log = free["log"].cpu().numpy()
+    replay = dict(noise_in=E.dev(log[:, :, 6 + m:]), q0_in=E.dev(log[:, 0, :6]), dq_in=free["dq_log"])
+    runs = {}
+    for quad in ("0", "1"):
+        monkeypatch.setenv("UVS_DENSE_QUAD", quad)
+        out = E.closed_loop(mk(E.noise_params(L.NOISE_NONE)), 0, B, want_log=True, want_state=True, want_trace=True,
+                            p_layout=L.P_DENSE, **replay)
+        runs[quad] = {k: v.cpu().numpy() for k, v in out.items()}
+    a, b = runs["0"], runs["1"]
+    assert np.array_equal(a["status"], b["status"]) and np.array_equal(a["frames"], b["frames"])
+    assert np.array_equal(a["flags"], b["flags"])
+    assert ((a["flags"] & L.FLAG_OUT_OF_VIEW) != 0).sum() >= 1
+    for t in range(B):
+        k = int(a["frames"][t])
+        for key in ("X_log", "P_log", "dq_log", "kappa_log"):
+            if k:
+                assert rel_err(b[key][t, :k], a[key][t, :k]) <= TOL_STEP, (nf, method, t, key)
+            assert not b[key][t, k:].any()                # frames a trial did not run stay untouched
+        assert np.array_equal(a["flags_log"][t], b["flags_log"][t])
+        assert rel_err(b["X"][t], a["X"][t]) <= TOL_STEP and rel_err(b["P"][t], a["P"][t]) <= TOL_STEP, (nf, method, t)
+        assert rel_err(b["log"][t], a["log"][t]) <= 1e-12
+    assert rel_err(b["stats"], a["stats"]) <= 1e-12
