@@ -9,24 +9,32 @@
 //
 // Here the two register populations live in different warps of a 5-warp CTA:
 //   warps 0..3  "covariance warps": warp g holds the off-diagonal blocks of filter g's P in registers for the whole trial
-//               and does the WIDE work of the frame: P += Q, A = P H^T, S0 = H A, the gain rows K = A S^-1 (two
-//               interleaved substitutions per lane, the factor read from shared memory), X += K nu, U, P -= K U^T; and,
-//               in the shadow of the chain warp's pseudo-inverse, the Philox / alpha-stable draws of the next 32 / M frames;
+//               and does the WIDE work of the frame: P += Q, A = P H^T, S0 = H A (from the registers that hold P_ik h),
+//               X += A y, the Gram matrix J^T J and J^T b of the IBVS normal equations (one entry per lane), P -= K U^T;
+//               and, through one non-inlined call every 32 / M frames, the Philox / alpha-stable draws of the next 32 / M
+//               frames (inlined, the samplers made ptxas park P in local memory for the whole frame loop);
 //   warp 4      "chain warp": group g = lanes 8g..8g+7 runs the SCALAR chains of filter g, one measurement row per lane,
 //               the four filters of the CTA in lockstep: plant (sincos, point in camera, pixel), hold logic, innovation,
-//               kernel weights, S = S0 + R_hat and its L D L^T, the IBVS pseudo-inverse (pinv_group with 8-lane groups),
-//               command, error integrals, logging — one instruction stream for four filters instead of four.
-// Neither role needs more than ~136 registers, so THREE CTAs = 12 filters are resident per SM (the shared-memory work
+//               kernel weights, S = S0 + R_hat and its L D L^T, the explicit S^-1 (one column per lane; the reference forms
+//               it too: K = P H^T inv(S), experiment.py:192,286-287), y = g S^-1 nu, the gain rows K = g A S^-1 and
+//               U = A + (A S^-1) D, the pseudo-inverse from the Gram matrix, command, finiteness, error integrals, log,
+//               trace — one instruction stream for four filters instead of four.
+// Neither role needs more than 128 registers, so THREE CTAs = 12 filters are resident per SM (the shared-memory work
 // space of a filter is unchanged, 14.5 KB), and the chain instructions are issued once per four filters.
 //
-// The roles exchange through the filter's shared-memory work space (DenseWS, as before) and meet at four CTA-wide named
-// barriers per frame:
-//   (4 / init) dq, alive, noise published | covariance: predict, A, S0        chain: noise, innovation, weights
-//   (1)        A, S0, nu, weights ready   |                                    chain: S, L D L^T -> Lc, ok
-//   (2)        factor ready               | covariance: gain rows, X, U
-//   (3)        X ready                    | covariance: P -= K U^T (+ noise)  chain: pinv, dq, integrals, next plant
-// Arithmetic: every quantity is computed by the same expression, in the same order, as in dense_step<M, METHOD, DEFER,
-// FAST> + ibvs_with_rank_update (dense.cuh), so the 1e-9 replay gate of tests/test_gpu_parity.py applies unchanged.
+// The roles exchange through the filter's shared-memory work space (DenseWS, as before) and meet at four named barriers
+// per frame; a role that only publishes at a barrier ARRIVES and goes on, the role that consumes WAITS:
+//   (4) dq, alive, done        | covariance: wait;  predict, A, S0        | chain: arrive;  log, integrals, integrate, NEXT
+//                              |                                          |        frame's plant, hold, innovation, weights
+//   (1) A, S0 / nu, weights, b | covariance: arrive;  (noise batch)       | chain: wait;  S, L D L^T, S^-1, y
+//   (2) S^-1, y, ok            | covariance: wait;  X += A y, Gram, J^T b | chain: arrive;  gain rows K, U
+//   (3) X, Gram / K, U         | covariance: wait;  P -= K U^T            | chain: wait;  pinv, command, finiteness
+// Barrier (4) sits right after the command.  A trial that ends because a feature left the image is found by the chain warp
+// after the covariance warp has started that frame's predict; the covariance warp restores the diagonal of P it saved (w.D).
+// Arithmetic: dense_step<M, METHOD, DEFER, FAST> + ibvs_with_rank_update (dense.cuh) with two re-associations inside the
+// 1e-9 gate: the gain rows come from the explicit S^-1 (not two substitutions per row), and X += A (g S^-1 nu) (not
+// (g A S^-1) nu).  tests/test_gpu_parity.py: the replay gate against experiment.py's own run, and
+// test_quad_kernel_matches_one_filter_per_warp_kernel.  DESIGN.md section 3.1 has the measurements behind every choice.
 //
 // Scope: the FAST configuration (Q = R = NULL, Joseph form, no scene plant: experiment.py:73-76,297 as hard-coded by the
 // reference), M >= 6, KF / IMCC-KF / GMCKF.  Everything else stays on dense_closed_loop_kernel.
@@ -127,7 +135,7 @@ __host__ __device__ constexpr size_t quad_smem_bytes(int T) {
 }
 
 // Gain rows by the CHAIN warp: lane gl of group g computes rows gl, gl + 8, ..., of filter g's K = gain_scale A S^-1,
-// RB rows at a time (independent accumulator sets: the chain warp holds no P, it has the registers), then X += K nu and
+// RB rows at a time (independent accumulator sets: the chain warp holds no P, it has the registers), and
 // U = A + (A S^-1) diag(ddiag).  The covariance warps do not take part: with P in their registers ptxas serialises this
 // phase on four temporaries (LDS -> DFMA -> LDS on the same registers, measured 6 900 cycles per frame for ~1 000 of work).
 template <int M, int RB>
