@@ -32,7 +32,7 @@ def _deps():
 
 def _extra_defs():
     names = ["UVS_DENSE_MINB", "UVS_DENSE_WARPS", "UVS_DENSE_L_SMEM", "UVS_DENSE_MAXNREG", "UVS_BD_MINB", "UVS_DENSE_FAST",
-             "UVS_PHASE_CLOCKS", "UVS_BD_PAD", "UVS_QUAD_MAXNREG", "UVS_DENSE_QUAD", "UVS_QUAD_GAIN_RB", "UVS_QUAD_RANK_UNROLL"]
+             "UVS_PHASE_CLOCKS", "UVS_BD_PAD", "UVS_QUAD_MAXNREG", "UVS_DENSE_QUAD", "UVS_QUAD_GAIN_RB", "UVS_QUAD_RANK_UNROLL", "UVS_BLK_STRIDE"]
     names += sorted(k for k in os.environ if k.startswith("UVS_OPT_"))
     return [f"-D{k}={os.environ[k]}" for k in names if os.environ.get(k)]
 

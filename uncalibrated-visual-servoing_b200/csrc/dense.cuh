@@ -7,7 +7,7 @@
 //   P    symmetric N x N, kept as its M(M+1)/2 lower 6x6 blocks.  The M(M-1)/2 OFF-DIAGONAL blocks
 //        live in REGISTERS for the whole trial — lane l < NOFF owns block (bi, bj) = offdiag_of_lane(l),
 //        36 doubles — and the M diagonal blocks live in shared memory (w.Pd, full 6x6 storage, both
-//        triangles identical, stride 38 doubles).
+//        triangles identical, kBlkStride = 36 doubles apart).
 //   At   (P H^T)^T, Kt = K^T, Ut = U^T : M x N in shared memory, "k-major", so a lane's 6 consecutive
 //        rows of one column are one 48-byte run (three LDS.128, broadcast across lanes sharing a
 //        block row).
@@ -33,7 +33,14 @@
 
 namespace uvs {
 
-constexpr int kBlkStride = 38;
+// Distance (doubles) between the 6 x 6 diagonal blocks in shared memory.  36 = unpadded: a row of a block is 48 B = three 16-B
+// bank groups, so eight consecutive rows (one per lane) fall on eight different bank groups whatever block they belong to
+// (3 is coprime with 8); the padded 38 of round 1 made the rows of neighbouring blocks collide (measured: 36 is +2.0 % on the
+// quad kernel, +0.9 % on the one-filter-per-warp kernel).
+#ifndef UVS_BLK_STRIDE
+#define UVS_BLK_STRIDE 36
+#endif
+constexpr int kBlkStride = UVS_BLK_STRIDE;
 
 template <int M>
 struct alignas(16) DenseConsts {          // per CTA
